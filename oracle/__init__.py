@@ -1,0 +1,219 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY (ctypes front-end of oracle/gustavson.c and oracle/_ref).
+
+May be imported only by tests/, ``__graft_entry__.smoke()`` and bench.py's
+``cpu_baseline`` / ``--impl reference`` legs.  The product package never imports it.
+
+* :class:`Oracle`    -- host Gustavson restatement (gcc + OpenMP), see gustavson.c for the
+  reference file:line each function follows.
+* :class:`Reference` -- the UNMODIFIED reference kernels rebuilt for sm_100
+  (oracle/_ref/libmhref.so, built by ``make -C oracle ref`` where /root/reference exists);
+  needs a GPU at call time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "_build", "liboracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libmhref.so")
+REF_TREE = "/root/reference"
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool = True) -> None:
+    """Compile the C restatement, and the reference where its tree is present."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    if ref and os.path.isdir(REF_TREE):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "-j8"])
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Oracle:
+    """Host Gustavson SpGEMM and the per-stage quantities of the reference pipeline."""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        L.orc_max_threads.restype = C.c_int
+        L.orc_intprod.restype = C.c_int64
+        L.orc_intprod.argtypes = [C.c_int, _i32p, _i32p, _i32p]
+        L.orc_row_intprod.argtypes = [C.c_int, _i32p, _i32p, _i32p, _i64p]
+        L.orc_mask_count.restype = C.c_int64
+        L.orc_mask_count.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _i32p]
+        L.orc_mask_fill.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _u32p]
+        L.orc_row_tileflop.argtypes = [C.c_int, _i32p, _i32p, _i32p, _i64p]
+        L.orc_symbolic.restype = C.c_int
+        L.orc_symbolic.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i64p]
+        L.orc_symbolic_mask.restype = C.c_int
+        L.orc_symbolic_mask.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _u32p, _i64p, _i64p]
+        for name, fp in (("orc_numeric_f64", _f64p), ("orc_numeric_f32", _f32p)):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, fp, _i32p, _i32p, fp, _i64p, _i32p, fp]
+        for name, fp in (("orc_compare_f64", _f64p), ("orc_compare_f32", _f32p)):
+            f = getattr(L, name)
+            f.restype = C.c_int64
+            f.argtypes = [C.c_int, _i64p, _i32p, fp, _i64p, _i32p, fp, C.c_double, C.POINTER(C.c_int64)]
+        self.L = L
+
+    @property
+    def threads(self) -> int:
+        return int(self.L.orc_max_threads())
+
+    def intprod(self, A, B) -> int:
+        return int(self.L.orc_intprod(A.M, A.ptr, A.col, B.ptr))
+
+    def row_intprod(self, A, B):
+        out = np.zeros(A.M, np.int64)
+        self.L.orc_row_intprod(A.M, A.ptr, A.col, B.ptr, out)
+        return out
+
+    def mask_matrix(self, B):
+        tileptr = np.zeros(B.M + 1, np.int32)
+        nt = int(self.L.orc_mask_count(B.M, B.N, B.ptr, B.col, tileptr))
+        tilecol = np.zeros(max(nt, 1), np.int32)
+        tilemask = np.zeros(max(nt, 1), np.uint32)
+        self.L.orc_mask_fill(B.M, B.N, B.ptr, B.col, tileptr, tilecol, tilemask)
+        return tileptr, tilecol[:nt], tilemask[:nt]
+
+    def row_tileflop(self, A, tileptr):
+        out = np.zeros(A.M, np.int64)
+        self.L.orc_row_tileflop(A.M, A.ptr, A.col, _c(tileptr, np.int32), out)
+        return out
+
+    def symbolic(self, A, B):
+        Cp = np.zeros(A.M + 1, np.int64)
+        rc = self.L.orc_symbolic(A.M, A.N, B.N, A.ptr, A.col, B.ptr, B.col, Cp)
+        assert rc == 0
+        return Cp
+
+    def symbolic_mask(self, A, B, mask=None):
+        tileptr, tilecol, tilemask = mask if mask is not None else self.mask_matrix(B)
+        Cp = np.zeros(A.M + 1, np.int64)
+        ctiles = np.zeros(A.M, np.int64)
+        tc = _c(tilecol, np.int32) if len(tilecol) else np.zeros(1, np.int32)
+        tm = _c(tilemask, np.uint32) if len(tilemask) else np.zeros(1, np.uint32)
+        rc = self.L.orc_symbolic_mask(A.M, B.N, A.ptr, A.col, _c(tileptr, np.int32), tc, tm, Cp, ctiles)
+        assert rc == 0
+        return Cp, ctiles
+
+    def numeric(self, A, B, Cp):
+        dt = A.val.dtype
+        nnz = int(Cp[-1])
+        Cc = np.zeros(max(nnz, 1), np.int32)
+        Cv = np.zeros(max(nnz, 1), dt)
+        f = self.L.orc_numeric_f64 if dt == np.float64 else self.L.orc_numeric_f32
+        rc = f(A.M, A.N, B.N, A.ptr, A.col, A.val, B.ptr, B.col, _c(B.val, dt), _c(Cp, np.int64), Cc, Cv)
+        assert rc == 0, "oracle numeric: row_ptr inconsistent with the structural product"
+        return Cc[:nnz], Cv[:nnz]
+
+    def spgemm(self, A, B):
+        """Host Gustavson C = A*B -> (Cp int64[M+1], Cc int32[nnz] ascending per row, Cv)."""
+        Cp = self.symbolic(A, B)
+        Cc, Cv = self.numeric(A, B, Cp)
+        return Cp, Cc, Cv
+
+    def compare(self, M, c1, c2, rtol):
+        """Number of mismatching entries between two (ptr, col, val) triples (0 == equal)."""
+        (p1, k1, v1), (p2, k2, v2) = c1, c2
+        dt = np.asarray(v1).dtype
+        f = self.L.orc_compare_f64 if dt == np.float64 else self.L.orc_compare_f32
+        first = C.c_int64(-1)
+
+        def pad(a, d):
+            a = _c(a, d)
+            return a if a.size else np.zeros(1, d)
+
+        bad = f(M, _c(p1, np.int64), pad(k1, np.int32), pad(v1, dt), _c(p2, np.int64), pad(k2, np.int32),
+                pad(v2, dt), float(rtol), C.byref(first))
+        return int(bad), int(first.value)
+
+
+class Reference:
+    """The reference's own GPU kernels (oracle/_ref/libmhref.so). Needs a CUDA device."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(
+                f"{REF_SO} missing: run `make -C oracle ref` where {REF_TREE} exists")
+        L = C.CDLL(REF_SO)
+        ip = C.POINTER(C.c_int)
+        dp = C.POINTER(C.c_double)
+        up = C.POINTER(C.c_uint)
+        L.mhref_free.argtypes = [C.c_void_p]
+        L.mhref_spgemm.restype = C.c_int
+        L.mhref_spgemm.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p,
+                                   C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(ip), C.POINTER(dp),
+                                   C.POINTER(C.c_int), dp, dp, _f64p,
+                                   C.c_void_p, C.POINTER(ip), C.POINTER(up)]
+        L.mhref_cusparse.restype = C.c_int
+        L.mhref_cusparse.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p,
+                                     C.c_int, C.c_int, _i32p, C.POINTER(ip), C.POINTER(dp),
+                                     C.POINTER(C.c_int), dp]
+        self.L = L
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(REF_SO)
+
+    def _take(self, p, n, dt):
+        if n == 0:
+            out = np.zeros(0, dt)
+        else:
+            out = np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True)
+        self.L.mhref_free(C.cast(p, C.c_void_p))
+        return out
+
+    def spgemm(self, A, B, reps=1, warmup=0, e2e_reps=0, want_mask=False):
+        """Run MH_spgemm. Returns dict(ptr, col, val, nnz, ms_device, ms_e2e, stage_ms[, mask])."""
+        assert A.val.dtype == np.float64, "the reference is compiled for VALUE_TYPE double"
+        Cp = np.zeros(A.M + 1, np.int32)
+        cc = C.POINTER(C.c_int)()
+        cv = C.POINTER(C.c_double)()
+        nnz = C.c_int(0)
+        msd, mse = C.c_double(0), C.c_double(0)
+        stage = np.zeros(7, np.float64)
+        tileptr = np.zeros(B.M + 1, np.int32)
+        tc = C.POINTER(C.c_int)()
+        tm = C.POINTER(C.c_uint)()
+        rc = self.L.mhref_spgemm(
+            A.M, A.N, B.N, A.ptr, A.col, A.val, B.ptr, B.col, B.val, reps, warmup, e2e_reps, Cp,
+            C.byref(cc), C.byref(cv), C.byref(nnz), C.byref(msd), C.byref(mse), stage,
+            tileptr.ctypes.data if want_mask else None,
+            C.byref(tc) if want_mask else None, C.byref(tm) if want_mask else None)
+        if rc != 0:
+            raise RuntimeError("reference MH_spgemm failed")
+        n = int(nnz.value)
+        out = dict(ptr=Cp, col=self._take(cc, n, np.int32), val=self._take(cv, n, np.float64), nnz=n,
+                   ms_device=float(msd.value), ms_e2e=float(mse.value), stage_ms=stage)
+        if want_mask:
+            nt = int(tileptr[-1])
+            out["mask"] = (tileptr, self._take(tc, nt, np.int32), self._take(tm, nt, np.uint32))
+        return out
+
+    def cusparse(self, A, B, reps=1, warmup=0):
+        Cp = np.zeros(A.M + 1, np.int32)
+        cc = C.POINTER(C.c_int)()
+        cv = C.POINTER(C.c_double)()
+        nnz = C.c_int(0)
+        msd = C.c_double(0)
+        rc = self.L.mhref_cusparse(A.M, A.N, B.N, A.ptr, A.col, A.val, B.ptr, B.col, B.val, reps, warmup,
+                                   Cp, C.byref(cc), C.byref(cv), C.byref(nnz), C.byref(msd))
+        if rc != 0:
+            raise RuntimeError("cuSPARSE SpGEMM failed")
+        n = int(nnz.value)
+        return dict(ptr=Cp, col=self._take(cc, n, np.int32), val=self._take(cv, n, np.float64), nnz=n,
+                    ms_device=float(msd.value))
