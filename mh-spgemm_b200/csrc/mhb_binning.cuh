@@ -1,0 +1,416 @@
+// mhb_binning.cuh -- kernel family 2: per-row intermediate-product counting, binning and
+// the exclusive scans, built on warp-level prefix sums (ballot / popc / shuffle scans).
+//
+// Replaces: k_calculate_flop, k_calculate_flop_tmp (inc/Form_mask_matrix_B.cuh:14-95),
+// k_binning1/k_binning2 + the host round trip of binning<TYPE> (inc/binning.cuh:67-155,
+// inc/MH_spgemm.cuh:26-43) and the three cub::DeviceScan::ExclusiveSum call sites
+// (inc/MH_spgemm.cuh:269,335; src/main.cu:55).
+//
+// Differences by design: bin offsets are computed on the device (no D2H/H2D per binning
+// call), the scatter is a stable partition (row ids ascending inside a bin, so runs are
+// reproducible -- the reference's atomic cursors are not), and one pass over A yields all
+// four per-row metrics (products, tile-flop, min / max column of the C row).
+#pragma once
+#include "mhb_common.cuh"
+
+namespace mhb
+{
+
+// ---------------------------------------------------------------------------------------
+// Exclusive scan of n ints (n up to 2^31) in two launches: block sums, then scan + apply.
+// ---------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+struct LoadInt
+{
+    const int *p;
+    __device__ __forceinline__ int operator()(long long i) const { return p[i]; }
+};
+struct LoadPopc
+{
+    const unsigned *p;
+    __device__ __forceinline__ int operator()(long long i) const { return __popc(p[i]); }
+};
+
+__device__ __forceinline__ long long block_reduce_sum(long long v, long long *sh /*32*/)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(kFull, v, o);
+    if (lane_id() == 0)
+        sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0;
+    if (threadIdx.x < 32)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            t += __shfl_xor_sync(kFull, t, o);
+        if (threadIdx.x == 0)
+            sh[0] = t;
+    }
+    __syncthreads();
+    t = sh[0];
+    __syncthreads();
+    return t;
+}
+
+template <class Load>
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(Load in, long long n, long long *blocksums)
+{
+    __shared__ long long sh[32];
+    long long base = (long long)blockIdx.x * kScanTile;
+    long long s = 0;
+#pragma unroll
+    for (int it = 0; it < kScanItems; ++it)
+    {
+        long long i = base + it * kScanThreads + threadIdx.x;
+        if (i < n)
+            s += in(i);
+    }
+    s = block_reduce_sum(s, sh);
+    if (threadIdx.x == 0)
+        blocksums[blockIdx.x] = s;
+}
+
+// out[i] = sum_{j<i} in(j) for i in [0, n); out[n] = total when write_total; *total64 = total.
+// In-place (out aliasing the input array) is safe: every item is read before any write of
+// the same block and blocks touch disjoint ranges.
+template <class Load>
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(Load in, long long n, const long long *blocksums,
+                                                             int nblocks, int *out, int write_total,
+                                                             long long *total64)
+{
+    __shared__ long long sh[32];
+    __shared__ int warp_tot[32];
+    // offset of this block = sum of the preceding block sums
+    long long pre = 0, all = 0;
+    for (int b = threadIdx.x; b < nblocks; b += kScanThreads)
+    {
+        long long v = blocksums[b];
+        all += v;
+        if (b < (int)blockIdx.x)
+            pre += v;
+    }
+    pre = block_reduce_sum(pre, sh);
+    if (blockIdx.x == gridDim.x - 1)
+    {
+        all = block_reduce_sum(all, sh);
+        if (threadIdx.x == 0)
+        {
+            if (total64)
+                *total64 = all;
+            if (write_total)
+                out[n] = sat_i32(all);
+        }
+    }
+    // thread t owns kScanItems consecutive items
+    long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int tsum = 0;
+#pragma unroll
+    for (int it = 0; it < kScanItems; ++it)
+    {
+        long long i = base + it;
+        v[it] = (i < n) ? in(i) : 0;
+        tsum += v[it];
+    }
+    // exclusive scan of tsum across the block: warp shuffle scan + warp totals
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        int t = __shfl_up_sync(kFull, incl, o);
+        if (lane_id() >= o)
+            incl += t;
+    }
+    if (lane_id() == 31)
+        warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        int w = warp_tot[threadIdx.x];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int t = __shfl_up_sync(kFull, wi, o);
+            if (lane_id() >= o)
+                wi += t;
+        }
+        warp_tot[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    long long run = pre + warp_tot[threadIdx.x >> 5] + (incl - tsum);
+#pragma unroll
+    for (int it = 0; it < kScanItems; ++it)
+    {
+        long long i = base + it;
+        if (i < n)
+            out[i] = sat_i32(run);
+        run += v[it];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Row metrics of C = A*B in one pass over A (G lanes per row, whole warp for long rows).
+//   arow[i] = {intermediate products (saturating), tile-flop, min column, max column}
+// also: symbolic bin id of the row, zero nnz for rows without products, global totals.
+// binfo[k] = {nnz, tiles, first column, last column} of B row k (written by family 1).
+// ---------------------------------------------------------------------------------------
+struct RowAcc
+{
+    long long ip;
+    long long tf;
+    int cmin;
+    int cmax;
+};
+
+__device__ __forceinline__ void row_acc_range(RowAcc &a, const int *__restrict__ Ac, const int4 *__restrict__ binfo,
+                                              int s, int e, int lane, int stride)
+{
+    for (int j = s + lane; j < e; j += stride)
+    {
+        int4 b = __ldg(&binfo[__ldg(&Ac[j])]);
+        a.ip += b.x;
+        a.tf += b.y;
+        if (b.x > 0)
+        {
+            a.cmin = min(a.cmin, b.z);
+            a.cmax = max(a.cmax, b.w);
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restrict__ Ap, const int *__restrict__ Ac,
+                                                      const int4 *__restrict__ binfo, int4 *__restrict__ arow,
+                                                      unsigned char *__restrict__ binid, int *__restrict__ counts,
+                                                      int *__restrict__ scal, int force_path)
+{
+    constexpr int kLong = 32 * G; // rows longer than this are walked by the whole warp
+    const int l = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool valid = gid < M;
+    const int row = valid ? (int)gid : 0;
+    int s = 0, e = 0;
+    if (valid)
+    {
+        s = __ldg(&Ap[row]);
+        e = __ldg(&Ap[row + 1]);
+    }
+    RowAcc a{0, 0, INT_MAX, -1};
+    const bool is_long = (e - s) > kLong;
+    if (!is_long)
+        row_acc_range(a, Ac, binfo, s, e, l, G);
+    if (G < 32)
+    {
+        a.ip = group_sum<G>(a.ip, gm);
+        a.tf = group_sum<G>(a.tf, gm);
+        a.cmin = group_min<G>(a.cmin, gm);
+        a.cmax = group_max<G>(a.cmax, gm);
+        // long rows: every lane of the warp helps, one row at a time
+        unsigned todo = __ballot_sync(kFull, is_long && l == 0);
+        while (todo)
+        {
+            int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int rs = __shfl_sync(kFull, s, src), re = __shfl_sync(kFull, e, src);
+            RowAcc w{0, 0, INT_MAX, -1};
+            row_acc_range(w, Ac, binfo, rs, re, lane_id(), 32);
+            w.ip = group_sum<32>(w.ip, kFull);
+            w.tf = group_sum<32>(w.tf, kFull);
+            w.cmin = group_min<32>(w.cmin, kFull);
+            w.cmax = group_max<32>(w.cmax, kFull);
+            if ((lane_id() & ~(G - 1)) == src)
+                a = w;
+        }
+    }
+    else
+    {
+        if (is_long)
+            row_acc_range(a, Ac, binfo, s, e, l, 32);
+        a.ip = group_sum<32>(a.ip, kFull);
+        a.tf = group_sum<32>(a.tf, kFull);
+        a.cmin = group_min<32>(a.cmin, kFull);
+        a.cmax = group_max<32>(a.cmax, kFull);
+    }
+    long long ip_tot = 0, tf_tot = 0;
+    int tf_max = 0;
+    if (valid && l == 0)
+    {
+        int ip = sat_i32(a.ip), tf = sat_i32(a.tf);
+        arow[row] = make_int4(ip, tf, a.cmin, a.cmax);
+        int b = mhb_classify_sym(ip, tf, a.cmin, a.cmax, force_path);
+        binid[row] = (unsigned char)b;
+        if (b == SB_EMPTY)
+            counts[row] = 0;
+        if (row == 0)
+            counts[M] = 0;
+        ip_tot = a.ip;
+        tf_tot = a.tf;
+        tf_max = tf;
+    }
+    // one atomic per warp for the totals
+    ip_tot = group_sum<32>(ip_tot, kFull);
+    tf_tot = group_sum<32>(tf_tot, kFull);
+    tf_max = group_max<32>(tf_max, kFull);
+    if (lane_id() == 0 && (ip_tot | tf_tot))
+    {
+        atomicAdd((unsigned long long *)(scal + SC_INTPROD_LO), (unsigned long long)ip_tot);
+        atomicAdd((unsigned long long *)(scal + SC_TILEFLOP_LO), (unsigned long long)tf_tot);
+        atomicMax(scal + SC_MAX_TILEFLOP, tf_max);
+    }
+}
+
+// Numeric bin id from the exact nnz of every C row (counts, before the scan).
+__global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restrict__ counts,
+                                                      const int4 *__restrict__ arow,
+                                                      unsigned char *__restrict__ binid, int *__restrict__ scal,
+                                                      int force_path)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0;
+    if (i < M)
+    {
+        n = counts[i];
+        int4 info = arow[i];
+        binid[i] = (unsigned char)mhb_classify_num(n, info.z, info.w, force_path);
+    }
+    n = group_max<32>(n, kFull);
+    if (lane_id() == 0 && n > 0)
+        atomicMax(scal + SC_MAX_ROWNNZ, n);
+}
+
+// ---------------------------------------------------------------------------------------
+// Stable binning: count per block, scan per bin across blocks on the device, scatter with
+// warp-level ranks (match_any + popc) and a warp prefix in shared memory.
+// blockhist layout: [bin][block].
+// ---------------------------------------------------------------------------------------
+constexpr int kBinThreads = 1024;
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_count(int M, const unsigned char *__restrict__ binid,
+                                                           int *__restrict__ blockhist, int nblocks)
+{
+    __shared__ int hist[MHB_MAX_BINS + 1];
+    if (threadIdx.x <= MHB_MAX_BINS)
+        hist[threadIdx.x] = 0;
+    __syncthreads();
+    int i = blockIdx.x * kBinThreads + threadIdx.x;
+    int b = (i < M) ? binid[i] : MHB_MAX_BINS;
+    unsigned peers = __match_any_sync(kFull, b);
+    if ((peers & lanemask_lt()) == 0)
+        atomicAdd(&hist[b], __popc(peers));
+    __syncthreads();
+    if (threadIdx.x < MHB_MAX_BINS)
+        blockhist[threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// One block: per bin, exclusive scan of the per-block counts; bin sizes / offsets to scal.
+__global__ void __launch_bounds__(1024) k_bin_offsets(int *__restrict__ blockhist, int nblocks, int nbins,
+                                                      int *__restrict__ size_out, int *__restrict__ off_out)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    int bin_base = 0;
+    for (int b = 0; b < nbins; ++b)
+    {
+        int *h = blockhist + (size_t)b * nblocks;
+        int start = carry; // == bin_base at this point
+        for (int c0 = 0; c0 < nblocks; c0 += 1024)
+        {
+            int i = c0 + threadIdx.x;
+            int v = (i < nblocks) ? h[i] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                int t = __shfl_up_sync(kFull, incl, o);
+                if (lane_id() >= o)
+                    incl += t;
+            }
+            if (lane_id() == 31)
+                warp_tot[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            if (threadIdx.x < 32)
+            {
+                int w = warp_tot[threadIdx.x], wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    int t = __shfl_up_sync(kFull, wi, o);
+                    if (lane_id() >= o)
+                        wi += t;
+                }
+                warp_tot[threadIdx.x] = wi - w;
+            }
+            __syncthreads();
+            int excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+            if (i < nblocks)
+                h[i] = excl;
+            __syncthreads();
+            if (threadIdx.x == 1023)
+                carry = excl + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+        {
+            size_out[b] = carry - start;
+            off_out[b] = start;
+        }
+        bin_base = carry;
+    }
+    if (threadIdx.x == 0)
+    {
+        off_out[nbins] = bin_base;
+        for (int b = nbins; b < MHB_MAX_BINS; ++b)
+        {
+            size_out[b] = 0;
+            off_out[b + 1] = bin_base;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(int M, const unsigned char *__restrict__ binid,
+                                                             const int *__restrict__ blockhist, int nblocks,
+                                                             int *__restrict__ bins)
+{
+    __shared__ int warpcnt[32][MHB_MAX_BINS + 1];
+    for (int t = threadIdx.x; t < 32 * (MHB_MAX_BINS + 1); t += kBinThreads)
+        (&warpcnt[0][0])[t] = 0;
+    __syncthreads();
+    int i = blockIdx.x * kBinThreads + threadIdx.x;
+    int w = threadIdx.x >> 5;
+    int b = (i < M) ? binid[i] : MHB_MAX_BINS;
+    unsigned peers = __match_any_sync(kFull, b);
+    int rank = __popc(peers & lanemask_lt());
+    if (rank == 0)
+        warpcnt[w][b] = __popc(peers);
+    __syncthreads();
+    // exclusive prefix over warps, per bin (column-wise), done by 32 x nbins threads
+    if (threadIdx.x < 32 * MHB_MAX_BINS)
+    {
+        // thread (bin = t / 32, lane = warp index): warp-level scan over the 32 warps
+        int bin = threadIdx.x >> 5, wl = threadIdx.x & 31;
+        int v = warpcnt[wl][bin], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            int t = __shfl_up_sync(kFull, incl, o);
+            if (wl >= o)
+                incl += t;
+        }
+        warpcnt[wl][bin] = incl - v;
+    }
+    __syncthreads();
+    if (i < M)
+        bins[blockhist[b * nblocks + blockIdx.x] + warpcnt[w][b] + rank] = i;
+}
+
+} // namespace mhb

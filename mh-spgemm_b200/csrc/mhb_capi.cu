@@ -1,0 +1,956 @@
+// mhb_capi.cu -- host orchestration of the four kernel families and the C ABI declared in
+// include/mhb_spgemm.h.  Replaces MH_spgemm (src/main.cu:12-72), the launchers of
+// inc/MH_spgemm.cuh and the Tool workspace (src/Tool.cu).
+//
+// Host-path design (vs the reference's 9 cudaMalloc, 12 stream creations, 7 blocking D2H
+// copies and 7 cudaDeviceSynchronize per call): one handle-owned, grow-only
+// workspace (no allocation in steady state), one stream, bin offsets computed on the
+// device, and exactly two small D2H reads per SpGEMM: the symbolic bin sizes, and
+// nnz(C) together with the numeric bin sizes (the hand-off the contract requires).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/mhb_spgemm.h"
+#include "mhb_binning.cuh"
+#include "mhb_common.cuh"
+#include "mhb_mask.cuh"
+#include "mhb_numeric.cuh"
+#include "mhb_symbolic.cuh"
+
+using namespace mhb;
+
+namespace
+{
+
+struct DevBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    bool grew = false;
+    cudaError_t ensure(size_t bytes)
+    {
+        grew = false;
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256; // a little slack so near-equal sizes do not regrow
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess)
+            return e;
+        cap = want;
+        grew = true;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess)
+            return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum Ev
+{
+    EV_START = 0,
+    EV_ALLOC,
+    EV_MASK,
+    EV_SYMBIN,
+    EV_SYM,
+    EV_NUMBIN,
+    EV_HANDOFF,
+    EV_NUM0,
+    EV_NUM1,
+    EV_COUNT
+};
+
+} // namespace
+
+struct mhb_context
+{
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_vals = nullptr, ev_ready = nullptr;
+    std::string err;
+    // options
+    int force_sym = 0, force_num = 0, verbose = 0;
+    // problem of the last symbolic call
+    bool have_pattern = false;
+    int M = 0, K = 0, N = 0, nnzA = 0, nnzB = 0;
+    const int *Ap = nullptr, *Ac = nullptr, *Bp = nullptr, *Bc = nullptr;
+    int *Cp = nullptr;
+    long long nnzC = 0;
+    int sym_off[MHB_MAX_BINS + 1] = {0}, num_off[MHB_MAX_BINS + 1] = {0};
+    int max_tileflop = 0, max_rownnz = 0;
+    // workspace
+    DevBuf flags, wordprefix, tileptr, tilecol, tilemask, binfo, arow, binid, bins_sym, bins_num, blockhist,
+        scan_tmp, scal, pool;
+    HostBuf h_scal;
+    // host-API staging
+    DevBuf sA_ptr, sA_col, sA_val, sB_ptr, sB_col, sB_val, sC_ptr, sC_col, sC_val;
+    HostBuf hC_ptr, hC_col, hC_val;
+    cudaEvent_t ev[EV_COUNT] = {nullptr};
+    bool ev_sym_valid = false, ev_num_valid = false;
+    mhb_timing timing{};
+    mhb_stats stats{};
+    int launches = 0;
+};
+
+namespace
+{
+
+int fail(mhb_context *h, int code, const std::string &msg)
+{
+    if (h)
+        h->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? MHB_ERR_NOMEM : MHB_ERR_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +    \
+                            std::to_string(__LINE__) + ")");                                             \
+    } while (0)
+
+#define LAUNCH(h, kern, grid, block, smem, ...)                                                          \
+    do                                                                                                   \
+    {                                                                                                    \
+        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);                                     \
+        ++(h)->launches;                                                                                 \
+        CU(cudaGetLastError());                                                                          \
+    } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class K>
+cudaError_t allow_smem(K kern, int bytes)
+{
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int log2_ceil(long long v)
+{
+    int l = 0;
+    while ((1LL << l) < v)
+        ++l;
+    return l;
+}
+
+// ---- exclusive scan helper: out[i] (i<n) exclusive prefix, out[n] total if write_total ----
+template <class Load>
+int run_scan(mhb_context *h, Load in, long long n, int *out, int write_total, long long *total64_dev)
+{
+    if (n <= 0)
+    {
+        if (total64_dev)
+            CU(cudaMemsetAsync(total64_dev, 0, sizeof(long long), h->stream));
+        if (write_total)
+            CU(cudaMemsetAsync(out, 0, sizeof(int), h->stream));
+        return MHB_OK;
+    }
+    int nb = cdiv(n, kScanTile);
+    long long *bs = h->scan_tmp.as<long long>();
+    LAUNCH(h, k_scan_blocksums<Load>, nb, kScanThreads, 0, in, n, bs);
+    LAUNCH(h, k_scan_apply<Load>, nb, kScanThreads, 0, in, n, bs, nb, out, write_total, total64_dev);
+    return MHB_OK;
+}
+
+// ---- stable binning of M rows by binid into `bins`; sizes/offsets to scal[size_at/off_at] ----
+int run_binning(mhb_context *h, int M, int nbins, int *bins, int size_at, int off_at)
+{
+    int *scal = h->scal.as<int>();
+    if (M <= 0)
+    {
+        CU(cudaMemsetAsync(scal + size_at, 0, sizeof(int) * MHB_MAX_BINS, h->stream));
+        CU(cudaMemsetAsync(scal + off_at, 0, sizeof(int) * (MHB_MAX_BINS + 1), h->stream));
+        return MHB_OK;
+    }
+    int nb = cdiv(M, kBinThreads);
+    const unsigned char *binid = h->binid.as<unsigned char>();
+    int *bh = h->blockhist.as<int>();
+    LAUNCH(h, k_bin_count, nb, kBinThreads, 0, M, binid, bh, nb);
+    LAUNCH(h, k_bin_offsets, 1, 1024, 0, bh, nb, nbins, scal + size_at, scal + off_at);
+    LAUNCH(h, k_bin_scatter, nb, kBinThreads, 0, M, binid, bh, nb, bins);
+    return MHB_OK;
+}
+
+int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
+{
+    *grew = false;
+    long long nW = ((long long)nnzB + 31) / 32;
+    struct Req
+    {
+        DevBuf *b;
+        size_t bytes;
+    } reqs[] = {
+        {&h->flags, (size_t)(nW + 1) * 4},
+        {&h->wordprefix, (size_t)(nW + 2) * 4},
+        {&h->tileptr, (size_t)(K + 2) * 4},
+        {&h->tilecol, (size_t)(nnzB + 1) * 4},
+        {&h->tilemask, (size_t)(nnzB + 1) * 4},
+        {&h->binfo, (size_t)(K + 1) * 16},
+        {&h->arow, (size_t)(M + 1) * 16},
+        {&h->binid, (size_t)(M + 1)},
+        {&h->bins_sym, (size_t)(M + 1) * 4},
+        {&h->bins_num, (size_t)(M + 1) * 4},
+        {&h->blockhist, (size_t)MHB_MAX_BINS * (size_t)(cdiv(std::max(M, 1), kBinThreads) + 1) * 4},
+        {&h->scan_tmp, (size_t)(cdiv(std::max<long long>(std::max<long long>(nW, M + 1), 1), kScanTile) + 2) * 8},
+        {&h->scal, (size_t)SC_COUNT * 4},
+    };
+    for (auto &r : reqs)
+    {
+        CU(r.b->ensure(r.bytes));
+        *grew |= r.b->grew;
+    }
+    CU(h->h_scal.ensure(SC_COUNT * 4));
+    return MHB_OK;
+}
+
+// ---- family 1 -----------------------------------------------------------------------------
+int build_mask_matrix(mhb_context *h, int K, int nnzB, const int *Bp, const int *Bc)
+{
+    const long long nnz = nnzB;
+    const long long nW = (nnz + 31) / 32;
+    unsigned *flags = h->flags.as<unsigned>();
+    int *wp = h->wordprefix.as<int>();
+    int *scal = h->scal.as<int>();
+    long long *ntiles_dev = reinterpret_cast<long long *>(scal + SC_NTILES_LO);
+    if (nnz > 0)
+    {
+        CU(cudaMemsetAsync(h->tilemask.p, 0, (size_t)nnz * 4, h->stream));
+        int grid = std::min(cdiv(nW * 32, 256), h->num_sms * 32);
+        LAUNCH(h, k_mask_flags, grid, 256, 0, Bc, nnz, nW, flags);
+        LAUNCH(h, k_mask_rowstarts, cdiv(K, 256), 256, 0, K, Bp, flags);
+    }
+    int rc = run_scan(h, LoadPopc{flags}, nW, wp, 0, ntiles_dev);
+    if (rc)
+        return rc;
+    LAUNCH(h, k_mask_tileptr, cdiv(K + 1, 256), 256, 0, K, nnz, Bp, Bc, flags, wp, ntiles_dev,
+           h->tileptr.as<int>(), h->binfo.as<int4>());
+    if (nnz > 0)
+    {
+        int grid = std::min(cdiv(nW * 32, 256), h->num_sms * 32);
+        LAUNCH(h, k_mask_fill, grid, 256, 0, Bc, nnz, nW, flags, wp, h->tilecol.as<int>(),
+               h->tilemask.as<unsigned>());
+    }
+    return MHB_OK;
+}
+
+int check_dev_error(mhb_context *h, const int *hs)
+{
+    if (hs[SC_ERROR] != DEVERR_NONE)
+        return fail(h, MHB_ERR_CUDA, "internal: a hash table filled up (device error flag " +
+                                         std::to_string(hs[SC_ERROR]) + ")");
+    return MHB_OK;
+}
+
+// ---- family 3 launches ------------------------------------------------------------------
+int launch_symbolic_bins(mhb_context *h)
+{
+    const int *off = h->sym_off;
+    auto n_of = [&](int b) { return off[b + 1] - off[b]; };
+    const int *bins = h->bins_sym.as<int>();
+    const int *tp = h->tileptr.as<int>();
+    const int *tc = h->tilecol.as<int>();
+    const unsigned *tm = h->tilemask.as<unsigned>();
+    const int4 *arow = h->arow.as<int4>();
+    int *scal = h->scal.as<int>();
+    int *counts = h->Cp;
+    const int cap_blocks = h->num_sms * 16;
+    int n;
+    if ((n = n_of(SB_BM_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kSymThreads / G;
+        LAUNCH(h, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               SB_BM_G8_WORDS);
+    }
+    if ((n = n_of(SB_BM_WARP)) > 0)
+    {
+        constexpr int G = 32, GPB = kSymThreads / G;
+        LAUNCH(h, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               SB_BM_WARP_WORDS);
+    }
+    if ((n = n_of(SB_BM_BLOCK)) > 0)
+    {
+        int words = std::min<long long>(SB_BM_BLOCK_WORDS, ((long long)h->N + 31) / 32 + 1);
+        LAUNCH(h, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
+               n, h->Ap, h->Ac, tp, tc, tm, arow, counts);
+    }
+    if ((n = n_of(SB_H_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kSymThreads / G;
+        LAUNCH(h, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               log2_ceil(SB_H_G8_SLOTS), scal);
+    }
+    if ((n = n_of(SB_H_WARP)) > 0)
+    {
+        constexpr int G = 32, GPB = kSymThreads / G;
+        LAUNCH(h, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               log2_ceil(SB_H_WARP_SLOTS), scal);
+    }
+    if ((n = n_of(SB_H_BLOCK_S)) > 0)
+        LAUNCH(h, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
+               bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal);
+    if ((n = n_of(SB_H_BLOCK_L)) > 0)
+        LAUNCH(h, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
+               bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal);
+    if ((n = n_of(SB_H_GLOBAL)) > 0)
+    {
+        long long nt = ((long long)h->N + 31) / 32;
+        long long ub = std::min<long long>(h->max_tileflop, nt);
+        long long slots = 1LL << std::max(10, log2_ceil(ub + (ub >> 1) + 1));
+        size_t slice = (size_t)slots * 2 * 4;
+        int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 30) / slice));
+        CU(h->pool.ensure(slice * nblk));
+        LAUNCH(h, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
+               arow, counts, 0, h->pool.as<int>(), slots, scal);
+    }
+    return MHB_OK;
+}
+
+// ---- family 4 launches ------------------------------------------------------------------
+template <typename T>
+int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv)
+{
+    const int *off = h->num_off;
+    auto n_of = [&](int b) { return off[b + 1] - off[b]; };
+    const int *bins = h->bins_num.as<int>();
+    const int4 *arow = h->arow.as<int4>();
+    int *scal = h->scal.as<int>();
+    const int cap_blocks = h->num_sms * 16;
+    const int *Ap = h->Ap, *Ac = h->Ac, *Bp = h->Bp, *Bc = h->Bc, *Cp = h->Cp;
+    int n;
+    if ((n = n_of(NB_WIN_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kNumGroupThreads / G;
+        auto kern = k_num_win_group<G, T>;
+        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
+               Cv, NB_WIN_G8_COLS);
+    }
+    if ((n = n_of(NB_WIN_WARP)) > 0)
+    {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_win_group<G, T>;
+        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               Cc, Cv, NB_WIN_WARP_COLS);
+    }
+    if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
+    {
+        int wcap = NB_WIN_BLOCK_S_COLS;
+        LAUNCH(h, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
+               bins + off[NB_WIN_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+    }
+    if ((n = n_of(NB_WIN_BLOCK_L)) > 0)
+    {
+        int wcap = (int)std::min<long long>(NB_WIN_BLOCK_L_COLS, (((long long)h->N + 31) / 32) * 32);
+        LAUNCH(h, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
+               bins + off[NB_WIN_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+    }
+    if ((n = n_of(NB_H_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv,
+               log2_ceil(NB_H_G8_SLOTS), scal);
+    }
+    if ((n = n_of(NB_H_WARP_S)) > 0)
+    {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
+               Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+    }
+    if ((n = n_of(NB_H_WARP_L)) > 0)
+    {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
+               Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS), scal);
+    }
+    if ((n = n_of(NB_H_BLOCK_S)) > 0)
+        LAUNCH(h, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
+               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
+               (unsigned char *)nullptr, 0LL, scal);
+    if ((n = n_of(NB_H_BLOCK_L)) > 0)
+        LAUNCH(h, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
+               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
+               (unsigned char *)nullptr, 0LL, scal);
+    if ((n = n_of(NB_H_GLOBAL)) > 0)
+    {
+        long long slots = 1LL << std::max(10, log2_ceil(2LL * h->max_rownnz));
+        size_t slice = (size_t)slots * (sizeof(T) + 4);
+        int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
+        CU(h->pool.ensure(slice * nblk));
+        LAUNCH(h, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc,
+               Cv, 0, h->pool.as<unsigned char>(), slots, scal);
+    }
+    return MHB_OK;
+}
+
+int set_kernel_attributes(mhb_context *h)
+{
+    CU(allow_smem(k_sym_bitmap_group<32>, 8 * SB_BM_WARP_WORDS * 4));
+    CU(allow_smem(k_sym_bitmap_block, MHB_SMEM_MAX - 256));
+    CU(allow_smem(k_sym_hash_block, 2 * SB_H_BLOCK_L_SLOTS * 4));
+    CU(allow_smem(k_num_win_group<8, double>, 32 * NB_WIN_G8_COLS * 8));
+    CU(allow_smem(k_num_win_group<32, double>, 8 * NB_WIN_WARP_COLS * 8));
+    CU(allow_smem(k_num_win_group<8, float>, 32 * NB_WIN_G8_COLS * 4));
+    CU(allow_smem(k_num_win_group<32, float>, 8 * NB_WIN_WARP_COLS * 4));
+    CU(allow_smem(k_num_win_block<double>, MHB_SMEM_MAX - 256));
+    CU(allow_smem(k_num_win_block<float>, MHB_SMEM_MAX - 256));
+    CU(allow_smem(k_num_hash_group<32, double>, 8 * NB_H_WARP_L_SLOTS * 12));
+    CU(allow_smem(k_num_hash_group<32, float>, 8 * NB_H_WARP_L_SLOTS * 8));
+    CU(allow_smem(k_num_hash_block<double>, NB_H_BLOCK_L_SLOTS * 12));
+    CU(allow_smem(k_num_hash_block<float>, NB_H_BLOCK_L_SLOTS * 8));
+    return MHB_OK;
+}
+
+float ev_ms(mhb_context *h, int a, int b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, int nnzB,
+                const int *Bp, const int *Bc, int *Cp, long long *nnzC_out)
+{
+    if (M < 0 || K < 0 || N < 0 || nnzA < 0 || nnzB < 0)
+        return fail(h, MHB_ERR_ARG, "negative dimension");
+    if (!Ap || !Bp || !Cp || (nnzA > 0 && !Ac) || (nnzB > 0 && !Bc))
+        return fail(h, MHB_ERR_ARG, "null CSR pointer");
+    CU(cudaSetDevice(h->device));
+    h->have_pattern = false;
+    h->launches = 0;
+    h->ev_sym_valid = h->ev_num_valid = false;
+    std::memset(&h->timing, 0, sizeof(h->timing));
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    h->M = M, h->K = K, h->N = N, h->nnzA = nnzA, h->nnzB = nnzB;
+    h->Ap = Ap, h->Ac = Ac, h->Bp = Bp, h->Bc = Bc, h->Cp = Cp;
+    CU(cudaEventRecord(h->ev[EV_START], h->stream));
+    bool grew = false;
+    int rc = ensure_workspace(h, M, K, nnzB, &grew);
+    if (rc)
+        return rc;
+    int *scal = h->scal.as<int>();
+    int *hs = h->h_scal.as<int>();
+    CU(cudaMemsetAsync(scal, 0, SC_COUNT * 4, h->stream));
+    CU(cudaEventRecord(h->ev[EV_ALLOC], h->stream));
+
+    // family 1: B mask matrix
+    rc = build_mask_matrix(h, K, nnzB, Bp, Bc);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(h->ev[EV_MASK], h->stream));
+
+    // family 2: row metrics + symbolic bins
+    if (M > 0)
+    {
+        double avg = (double)nnzA / M;
+        if (avg > 12.0)
+            LAUNCH(h, k_arow_metrics<32>, cdiv((long long)M * 32, 256), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
+                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
+        else
+            LAUNCH(h, k_arow_metrics<4>, cdiv((long long)M * 4, 256), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
+                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
+    }
+    else
+        CU(cudaMemsetAsync(Cp, 0, sizeof(int), h->stream));
+    rc = run_binning(h, M, SB_COUNT, h->bins_sym.as<int>(), SC_SYM_SIZE, SC_SYM_OFF);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(hs, scal, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[EV_SYMBIN], h->stream));
+    CU(cudaStreamSynchronize(h->stream)); // read #1: symbolic bin sizes
+    std::memcpy(h->sym_off, hs + SC_SYM_OFF, sizeof(h->sym_off));
+    h->max_tileflop = hs[SC_MAX_TILEFLOP];
+    std::memcpy(&h->stats.intprod, hs + SC_INTPROD_LO, 8);
+    std::memcpy(&h->stats.tileflop, hs + SC_TILEFLOP_LO, 8);
+    std::memcpy(&h->stats.ntiles_B, hs + SC_NTILES_LO, 8);
+    std::memcpy(h->stats.sym_bin_size, hs + SC_SYM_SIZE, sizeof(int) * MHB_MAX_BINS);
+
+    // family 3: nnz per C row
+    rc = launch_symbolic_bins(h);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(h->ev[EV_SYM], h->stream));
+
+    // family 2 again: numeric bins from the exact row sizes, then the row-offset scan
+    if (M > 0)
+        LAUNCH(h, k_classify_num, cdiv(M, 256), 256, 0, M, Cp, h->arow.as<int4>(), h->binid.as<unsigned char>(),
+               scal, h->force_num);
+    rc = run_binning(h, M, NB_COUNT, h->bins_num.as<int>(), SC_NUM_SIZE, SC_NUM_OFF);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(h->ev[EV_NUMBIN], h->stream));
+    rc = run_scan(h, LoadInt{Cp}, M, Cp, 1, reinterpret_cast<long long *>(scal + SC_NNZC_LO));
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(hs, scal, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev[EV_HANDOFF], h->stream));
+    CU(cudaStreamSynchronize(h->stream)); // read #2: nnz(C) + numeric bin sizes (the hand-off)
+    rc = check_dev_error(h, hs);
+    if (rc)
+        return rc;
+    std::memcpy(h->num_off, hs + SC_NUM_OFF, sizeof(h->num_off));
+    h->max_rownnz = hs[SC_MAX_ROWNNZ];
+    std::memcpy(&h->nnzC, hs + SC_NNZC_LO, 8);
+    std::memcpy(h->stats.num_bin_size, hs + SC_NUM_SIZE, sizeof(int) * MHB_MAX_BINS);
+    h->stats.nnzC = h->nnzC;
+    h->stats.gpu_launches = h->launches;
+    *nnzC_out = h->nnzC;
+    h->ev_sym_valid = true;
+    h->timing.mem_alloc = ev_ms(h, EV_START, EV_ALLOC);
+    h->timing.form_mask_matrix_B = ev_ms(h, EV_ALLOC, EV_MASK);
+    h->timing.symbolic_binning = ev_ms(h, EV_MASK, EV_SYMBIN);
+    h->timing.calculate_C_nnz = ev_ms(h, EV_SYMBIN, EV_SYM);
+    h->timing.numeric_binning = ev_ms(h, EV_SYM, EV_NUMBIN);
+    h->timing.malloc_C_col_val = ev_ms(h, EV_NUMBIN, EV_HANDOFF);
+    h->timing.total = ev_ms(h, EV_START, EV_HANDOFF);
+    if (h->nnzC > (long long)INT_MAX)
+        return fail(h, MHB_ERR_OVERFLOW,
+                    "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the int32 CSR contract; shard the rows of A");
+    h->have_pattern = true;
+    if (h->verbose)
+        std::printf("C.nnz = %lld\n", h->nnzC); // the reference's print (src/main.cu:58), opt-in
+    return MHB_OK;
+}
+
+template <typename T>
+int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sync)
+{
+    if (!h->have_pattern)
+        return fail(h, MHB_ERR_ARG, "mhb_numeric called without a successful mhb_symbolic");
+    if (h->nnzC > 0 && (!Av || !Bv || !Cc || !Cv))
+        return fail(h, MHB_ERR_ARG, "null value / output pointer");
+    CU(cudaSetDevice(h->device));
+    int before = h->launches;
+    CU(cudaEventRecord(h->ev[EV_NUM0], h->stream));
+    int rc = launch_numeric_bins<T>(h, Av, Bv, Cc, Cv);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(h->ev[EV_NUM1], h->stream));
+    h->stats.gpu_launches = h->launches;
+    (void)before;
+    if (sync)
+    {
+        int *hs = h->h_scal.as<int>();
+        CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        rc = check_dev_error(h, hs);
+        if (rc)
+            return rc;
+        h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
+        if (h->ev_sym_valid)
+            h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
+    }
+    return MHB_OK;
+}
+
+template <typename T>
+int do_spgemm(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, const T *Av, int nnzB,
+              const int *Bp, const int *Bc, const T *Bv, int **Cp, int **Cc, T **Cv, long long *nnzC)
+{
+    if (!Cp || !Cc || !Cv || !nnzC)
+        return fail(h, MHB_ERR_ARG, "null output pointer");
+    *Cp = nullptr, *Cc = nullptr, *Cv = nullptr;
+    CU(cudaMalloc((void **)Cp, sizeof(int) * ((size_t)M + 1)));
+    int rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, *Cp, nnzC);
+    if (rc == MHB_OK)
+    {
+        size_t n = (size_t)std::max<long long>(*nnzC, 1);
+        cudaError_t e1 = cudaMalloc((void **)Cc, sizeof(int) * n);
+        cudaError_t e2 = cudaMalloc((void **)Cv, sizeof(T) * n);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+            rc = fail(h, MHB_ERR_NOMEM, "cudaMalloc of C.col / C.val failed");
+        else
+            rc = do_numeric<T>(h, Av, Bv, *Cc, *Cv, true);
+    }
+    if (rc != MHB_OK)
+    {
+        cudaFree(*Cp), cudaFree(*Cc), cudaFree(*Cv);
+        *Cp = nullptr, *Cc = nullptr, *Cv = nullptr;
+    }
+    return rc;
+}
+
+template <typename T>
+int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const int *hAc, const T *hAv,
+                   const int *hBp, const int *hBc, const T *hBv, const int **hCp, const int **hCc,
+                   const T **hCv, long long *nnzC)
+{
+    if (!hAp || !hBp || !hCp || !hCc || !hCv || !nnzC)
+        return fail(h, MHB_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(h->device));
+    const int nnzA = hAp[M], nnzB = hBp[K];
+    const bool alias = (hAp == hBp && hAc == hBc && (const void *)hAv == (const void *)hBv && M == K);
+    cudaStream_t st = h->stream;
+    CU(h->sA_ptr.ensure(((size_t)M + 1) * 4));
+    CU(h->sA_col.ensure(((size_t)nnzA + 1) * 4));
+    CU(h->sA_val.ensure(((size_t)nnzA + 1) * sizeof(T)));
+    CU(h->sC_ptr.ensure(((size_t)M + 2) * 4));
+    CU(h->hC_ptr.ensure(((size_t)M + 2) * 4));
+    // index arrays first: the symbolic phase needs no values, so their upload overlaps it
+    CU(cudaMemcpyAsync(h->sA_ptr.p, hAp, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->sA_col.p, hAc, (size_t)nnzA * 4, cudaMemcpyHostToDevice, st));
+    const int *dBp = h->sA_ptr.as<int>(), *dBc = h->sA_col.as<int>();
+    const T *dBv = h->sA_val.as<T>();
+    if (!alias)
+    {
+        CU(h->sB_ptr.ensure(((size_t)K + 1) * 4));
+        CU(h->sB_col.ensure(((size_t)nnzB + 1) * 4));
+        CU(h->sB_val.ensure(((size_t)nnzB + 1) * sizeof(T)));
+        CU(cudaMemcpyAsync(h->sB_ptr.p, hBp, ((size_t)K + 1) * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->sB_col.p, hBc, (size_t)nnzB * 4, cudaMemcpyHostToDevice, st));
+        dBp = h->sB_ptr.as<int>(), dBc = h->sB_col.as<int>(), dBv = h->sB_val.as<T>();
+    }
+    // values go up on a second stream: the symbolic phase reads no values, so this copy
+    // overlaps the mask build / binning / symbolic kernels and numeric waits on ev_vals
+    CU(cudaEventRecord(h->ev_ready, st)); // staging buffers are free once earlier work on st is done
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+    CU(cudaMemcpyAsync(h->sA_val.p, hAv, (size_t)nnzA * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
+    if (!alias)
+        CU(cudaMemcpyAsync(h->sB_val.p, hBv, (size_t)nnzB * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->ev_vals, h->copy_stream));
+    int rc = do_symbolic(h, M, K, N, nnzA, h->sA_ptr.as<int>(), h->sA_col.as<int>(), nnzB, dBp, dBc,
+                         h->sC_ptr.as<int>(), nnzC);
+    if (rc)
+        return rc;
+    size_t n = (size_t)std::max<long long>(*nnzC, 1);
+    CU(h->sC_col.ensure(n * 4));
+    CU(h->sC_val.ensure(n * sizeof(T)));
+    CU(h->hC_col.ensure(n * 4));
+    CU(h->hC_val.ensure(n * sizeof(T)));
+    CU(cudaMemcpyAsync(h->hC_ptr.p, h->sC_ptr.p, ((size_t)M + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamWaitEvent(st, h->ev_vals, 0));
+    rc = do_numeric<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false);
+    if (rc)
+        return rc;
+    CU(cudaMemcpyAsync(h->hC_col.p, h->sC_col.p, (size_t)*nnzC * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->hC_val.p, h->sC_val.p, (size_t)*nnzC * sizeof(T), cudaMemcpyDeviceToHost, st));
+    int *hs = h->h_scal.as<int>();
+    CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    rc = check_dev_error(h, hs);
+    if (rc)
+        return rc;
+    h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
+    h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
+    *hCp = h->hC_ptr.as<int>();
+    *hCc = h->hC_col.as<int>();
+    *hCv = h->hC_val.as<T>();
+    return MHB_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C"
+{
+
+    const char *mhb_version(void) { return "mhb-spgemm 0.1 (sm_100a)"; }
+
+    int mhb_create(mhb_handle_t *out, int device)
+    {
+        if (!out)
+            return MHB_ERR_ARG;
+        *out = nullptr;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+            return MHB_ERR_CUDA; // no CPU fallback: without a CUDA device the library refuses to run
+        mhb_context *h = new mhb_context();
+        h->device = device;
+        auto bail = [&](int code) {
+            delete h;
+            return code;
+        };
+        if (cudaSetDevice(device) != cudaSuccess)
+            return bail(MHB_ERR_CUDA);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+            return bail(MHB_ERR_CUDA);
+        h->num_sms = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+            return bail(MHB_ERR_CUDA);
+        h->stream = h->own_stream;
+        if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_vals, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming) != cudaSuccess)
+            return bail(MHB_ERR_CUDA);
+        for (auto &e : h->ev)
+            if (cudaEventCreate(&e) != cudaSuccess)
+                return bail(MHB_ERR_CUDA);
+        if (set_kernel_attributes(h) != MHB_OK)
+        {
+            std::fprintf(stderr, "mhb_create: %s\n", h->err.c_str());
+            return bail(MHB_ERR_CUDA);
+        }
+        *out = h;
+        return MHB_OK;
+    }
+
+    int mhb_destroy(mhb_handle_t h)
+    {
+        if (!h)
+            return MHB_OK;
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
+                          &h->binid, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
+                          &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
+                          &h->sC_col, &h->sC_val})
+            b->release();
+        for (HostBuf *b : {&h->h_scal, &h->hC_ptr, &h->hC_col, &h->hC_val})
+            b->release();
+        for (auto &e : h->ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (h->ev_vals)
+            cudaEventDestroy(h->ev_vals);
+        if (h->ev_ready)
+            cudaEventDestroy(h->ev_ready);
+        if (h->copy_stream)
+            cudaStreamDestroy(h->copy_stream);
+        if (h->own_stream)
+            cudaStreamDestroy(h->own_stream);
+        delete h;
+        return MHB_OK;
+    }
+
+    const char *mhb_last_error(mhb_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+    int mhb_set_stream(mhb_handle_t h, void *cuda_stream)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+        return MHB_OK;
+    }
+
+    int mhb_set_option(mhb_handle_t h, const char *key, long long value)
+    {
+        if (!h || !key)
+            return MHB_ERR_ARG;
+        std::string k(key);
+        if (k == "force_sym_path")
+            h->force_sym = (int)value;
+        else if (k == "force_num_path")
+            h->force_num = (int)value;
+        else if (k == "verbose")
+            h->verbose = (int)value;
+        else
+            return fail(h, MHB_ERR_ARG, "unknown option " + k);
+        return MHB_OK;
+    }
+
+    int mhb_symbolic(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col, int nnzB,
+                     const int *dB_ptr, const int *dB_col, int *dC_ptr, long long *nnzC)
+    {
+        if (!h || !nnzC)
+            return MHB_ERR_ARG;
+        return do_symbolic(h, M, K, N, nnzA, dA_ptr, dA_col, nnzB, dB_ptr, dB_col, dC_ptr, nnzC);
+    }
+
+    int mhb_numeric_f64(mhb_handle_t h, const double *dA_val, const double *dB_val, int *dC_col, double *dC_val)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_numeric<double>(h, dA_val, dB_val, dC_col, dC_val, true);
+    }
+    int mhb_numeric_f32(mhb_handle_t h, const float *dA_val, const float *dB_val, int *dC_col, float *dC_val)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_numeric<float>(h, dA_val, dB_val, dC_col, dC_val, true);
+    }
+
+    int mhb_spgemm_f64(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                       const double *dA_val, int nnzB, const int *dB_ptr, const int *dB_col, const double *dB_val,
+                       int **dC_ptr, int **dC_col, double **dC_val, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm<double>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
+                                 dC_col, dC_val, nnzC);
+    }
+    int mhb_spgemm_f32(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                       const float *dA_val, int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
+                       int **dC_ptr, int **dC_col, float **dC_val, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm<float>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
+                                dC_col, dC_val, nnzC);
+    }
+    int mhb_device_free(void *dptr) { return cudaFree(dptr) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA; }
+    int mhb_device_alloc(void **dptr, size_t bytes)
+    {
+        if (!dptr)
+            return MHB_ERR_ARG;
+        return cudaMalloc(dptr, bytes ? bytes : 1) == cudaSuccess ? MHB_OK : MHB_ERR_NOMEM;
+    }
+    int mhb_memcpy_h2d(void *dptr, const void *hptr, size_t bytes)
+    {
+        return cudaMemcpy(dptr, hptr, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA;
+    }
+    int mhb_memcpy_d2h(void *hptr, const void *dptr, size_t bytes)
+    {
+        return cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA;
+    }
+
+    int mhb_spgemm_host_f64(mhb_handle_t h, int M, int K, int N, const int *hA_ptr, const int *hA_col,
+                            const double *hA_val, const int *hB_ptr, const int *hB_col, const double *hB_val,
+                            const int **hC_ptr, const int **hC_col, const double **hC_val, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm_host<double>(h, M, K, N, hA_ptr, hA_col, hA_val, hB_ptr, hB_col, hB_val, hC_ptr, hC_col,
+                                      hC_val, nnzC);
+    }
+    int mhb_spgemm_host_f32(mhb_handle_t h, int M, int K, int N, const int *hA_ptr, const int *hA_col,
+                            const float *hA_val, const int *hB_ptr, const int *hB_col, const float *hB_val,
+                            const int **hC_ptr, const int **hC_col, const float **hC_val, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm_host<float>(h, M, K, N, hA_ptr, hA_col, hA_val, hB_ptr, hB_col, hB_val, hC_ptr, hC_col,
+                                     hC_val, nnzC);
+    }
+
+    int mhb_host_alloc(void **hptr, size_t bytes)
+    {
+        if (!hptr)
+            return MHB_ERR_ARG;
+        return cudaMallocHost(hptr, bytes ? bytes : 1) == cudaSuccess ? MHB_OK : MHB_ERR_NOMEM;
+    }
+    int mhb_host_free(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA; }
+
+    int mhb_form_mask_matrix_B(mhb_handle_t h, int K, int N, int nnzB, const int *dB_ptr, const int *dB_col,
+                               const int **d_tileptr, const int **d_tilecol, const unsigned **d_tilemask,
+                               long long *ntiles)
+    {
+        if (!h || !d_tileptr || !d_tilecol || !d_tilemask || !ntiles)
+            return MHB_ERR_ARG;
+        if (K < 0 || N < 0 || nnzB < 0 || !dB_ptr || (nnzB > 0 && !dB_col))
+            return fail(h, MHB_ERR_ARG, "bad B");
+        CU(cudaSetDevice(h->device));
+        h->have_pattern = false;
+        h->launches = 0;
+        bool grew;
+        int rc = ensure_workspace(h, 0, K, nnzB, &grew);
+        if (rc)
+            return rc;
+        CU(cudaMemsetAsync(h->scal.p, 0, SC_COUNT * 4, h->stream));
+        rc = build_mask_matrix(h, K, nnzB, dB_ptr, dB_col);
+        if (rc)
+            return rc;
+        int *hs = h->h_scal.as<int>();
+        CU(cudaMemcpyAsync(hs, h->scal.p, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        std::memcpy(ntiles, hs + SC_NTILES_LO, 8);
+        *d_tileptr = h->tileptr.as<int>();
+        *d_tilecol = h->tilecol.as<int>();
+        *d_tilemask = h->tilemask.as<unsigned>();
+        h->stats.gpu_launches = h->launches;
+        return MHB_OK;
+    }
+
+    int mhb_get_row_info(mhb_handle_t h, const int **d_row_info)
+    {
+        if (!h || !d_row_info)
+            return MHB_ERR_ARG;
+        if (!h->have_pattern)
+            return fail(h, MHB_ERR_ARG, "no symbolic result on this handle");
+        *d_row_info = h->arow.as<int>();
+        return MHB_OK;
+    }
+
+    int mhb_get_bins(mhb_handle_t h, int which, int *nbins, const int **d_bins, int *h_bin_offset)
+    {
+        if (!h || !nbins || !d_bins || !h_bin_offset)
+            return MHB_ERR_ARG;
+        if (!h->have_pattern)
+            return fail(h, MHB_ERR_ARG, "no symbolic result on this handle");
+        *nbins = which == 0 ? (int)SB_COUNT : (int)NB_COUNT;
+        *d_bins = which == 0 ? h->bins_sym.as<int>() : h->bins_num.as<int>();
+        std::memcpy(h_bin_offset, which == 0 ? h->sym_off : h->num_off, sizeof(int) * (MHB_MAX_BINS + 1));
+        return MHB_OK;
+    }
+
+    int mhb_get_timing(mhb_handle_t h, mhb_timing *out)
+    {
+        if (!h || !out)
+            return MHB_ERR_ARG;
+        *out = h->timing;
+        return MHB_OK;
+    }
+    int mhb_get_stats(mhb_handle_t h, mhb_stats *out)
+    {
+        if (!h || !out)
+            return MHB_ERR_ARG;
+        *out = h->stats;
+        return MHB_OK;
+    }
+
+} // extern "C"

@@ -1,0 +1,118 @@
+// mhb_common.cuh -- device helpers shared by the four kernel families.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include "mhb_config.h"
+
+namespace mhb
+{
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ unsigned lanemask_le()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Lanes of the G-wide group this thread belongs to (G = 8 or 32).
+template <int G>
+__device__ __forceinline__ unsigned group_mask()
+{
+    if constexpr (G == 32)
+        return kFull;
+    else
+        return ((1u << G) - 1u) << (lane_id() & ~(G - 1));
+}
+
+template <int G, typename T>
+__device__ __forceinline__ T group_sum(T v, unsigned gm)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+        v += __shfl_xor_sync(gm, v, o, G);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_min(int v, unsigned gm)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+        v = min(v, __shfl_xor_sync(gm, v, o, G));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_max(int v, unsigned gm)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1)
+        v = max(v, __shfl_xor_sync(gm, v, o, G));
+    return v;
+}
+
+// Fibonacci hashing into a power-of-two table of 2^logS slots.  The reference hashes with
+// (key*107) % prime and cumulative-square probing (inc/common.h:72, inc/numeric.cuh:233),
+// which reaches only ~67 % of the slots; multiplicative hashing with
+// linear probing over a power-of-two table is a full cycle and needs no integer modulo.
+__device__ __forceinline__ unsigned hash_slot(unsigned key, int logS)
+{
+    return (key * 2654435761u) >> (32 - logS);
+}
+
+__device__ __forceinline__ int sat_i32(long long v) { return v > INT_MAX ? INT_MAX : (int)v; }
+
+// "Never written" marker of the dense numeric window: a signalling-NaN bit pattern.  Every
+// value stored into the window is the result of a multiply or fused multiply-add, and the
+// FPU never produces a signalling NaN, so the marker cannot collide with a real value --
+// entries whose products cancel to 0.0 (or are NaN/Inf) stay structurally present, as in
+// the reference (inc/numeric.cuh:237-241 accumulates without testing for zero).
+template <typename T>
+struct Unset;
+template <>
+struct Unset<double>
+{
+    static __device__ __forceinline__ double value() { return __longlong_as_double(0x7FF0000000000001LL); }
+    static __device__ __forceinline__ bool is(double v) { return __double_as_longlong(v) == 0x7FF0000000000001LL; }
+};
+template <>
+struct Unset<float>
+{
+    static __device__ __forceinline__ float value() { return __int_as_float(0x7F800001); }
+    static __device__ __forceinline__ bool is(float v) { return __float_as_int(v) == 0x7F800001; }
+};
+
+// error flags raised by kernels (checked by the host at the next synchronisation point)
+enum DevError
+{
+    DEVERR_NONE = 0,
+    DEVERR_TABLE_FULL = 1, // a hash table filled up: row metrics and table ladder disagree
+};
+
+// Layout of the device scalar block (ints) mirrored to pinned host memory.
+enum Scalar
+{
+    SC_INTPROD_LO = 0, // unsigned long long at [0..1]
+    SC_TILEFLOP_LO = 2, // unsigned long long at [2..3]
+    SC_NTILES_LO = 4,   // long long at [4..5]
+    SC_NNZC_LO = 6,     // long long at [6..7]
+    SC_MAX_TILEFLOP = 8,
+    SC_MAX_ROWNNZ = 9,
+    SC_ERROR = 10,
+    SC_SYM_SIZE = 16,               // MHB_MAX_BINS ints
+    SC_SYM_OFF = 32,                // MHB_MAX_BINS + 1 ints
+    SC_NUM_SIZE = 64,               // MHB_MAX_BINS ints
+    SC_NUM_OFF = 80,                // MHB_MAX_BINS + 1 ints
+    SC_COUNT = 128
+};
+
+} // namespace mhb

@@ -1,0 +1,299 @@
+// mhb_symbolic.cuh -- kernel family 3: the symbolic nnz(C) pass.
+//
+// Replaces Calculate_C_nnz (inc/MH_spgemm.cuh:297-362) and its 10 kernels
+// (inc/Calculate_C_nnz.cuh): nnz of every row of C = A*B from B's mask matrix.
+//
+// The reference hashes B's tiles twice per C row (count distinct C tiles, re-bin, then OR
+// the masks and popc).  Here one traversal suffices, and two accumulators are used:
+//
+//  * BITMAP (sm_100a: 227 KB of shared memory holds a 1.8 M-column bitmap): when the C
+//    row spans few 32-column words relative to its work, the row's occupancy bitmap lives
+//    in shared memory, word index = tile column - first tile column, and every B tile is
+//    one OR.  nnz = popcount of the bitmap.  No keys, no probing, no second pass.
+//  * TILE HASH (key = tile column, value = OR of masks) in shared memory sized per bin,
+//    with a global-memory table for rows whose tile count exceeds 12 K.
+//
+// Group kernels (8 lanes or a warp per row) walk A's row one B row at a time; the tiles of
+// one B row are distinct, so lanes never touch the same word/slot in the same step and the
+// OR is a plain read-modify-write ordered by __syncwarp -- no shared-memory atomics.
+// Block kernels (one block per row, warps on different B rows) use atomicOr.
+#pragma once
+#include "mhb_common.cuh"
+
+namespace mhb
+{
+
+constexpr int kSymThreads = 256;
+
+// ---- bitmap, G lanes per row -----------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kSymThreads)
+    k_sym_bitmap_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                       const int *__restrict__ Ac, const int *__restrict__ tileptr,
+                       const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
+                       const int4 *__restrict__ arow, int *__restrict__ counts, int wcap)
+{
+    extern __shared__ unsigned sm_u[];
+    constexpr int GPB = kSymThreads / G;
+    const int g = threadIdx.x / G, l = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    unsigned *bm = sm_u + (size_t)g * wcap;
+    for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
+    {
+        const int row = rows[r];
+        const int4 info = arow[row];
+        const int tbase = info.z >> MHB_TILE_SHIFT;
+        const int wt = (info.w >> MHB_TILE_SHIFT) - tbase + 1;
+        for (int w = l; w < wt; w += G)
+            bm[w] = 0u;
+        __syncwarp(gm);
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        for (int j0 = s; j0 < e; j0 += G)
+        {
+            int ts = 0, te = 0;
+            if (j0 + l < e)
+            {
+                int k = __ldg(&Ac[j0 + l]);
+                ts = __ldg(&tileptr[k]);
+                te = __ldg(&tileptr[k + 1]);
+            }
+            const int cnt = min(G, e - j0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                const int qs = __shfl_sync(gm, ts, i, G), qe = __shfl_sync(gm, te, i, G);
+                for (int q = qs + l; q < qe; q += G)
+                {
+                    const int w = __ldg(&tilecol[q]) - tbase;
+                    bm[w] |= __ldg(&tilemask[q]);
+                }
+                __syncwarp(gm);
+            }
+        }
+        int c = 0;
+        for (int w = l; w < wt; w += G)
+            c += __popc(bm[w]);
+        c = group_sum<G>(c, gm);
+        if (l == 0)
+            counts[row] = c;
+        __syncwarp(gm);
+    }
+}
+
+__device__ __forceinline__ int block_sum_int(int v, int *sh /*32*/)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads(); // sh may still be read from a previous call
+    if (lane_id() == 0)
+        sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w)
+        t += sh[w];
+    return t;
+}
+
+// ---- bitmap, one block per row (Wt up to 57 344 words) ---------------------------------
+__global__ void __launch_bounds__(kSymThreads)
+    k_sym_bitmap_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                       const int *__restrict__ Ac, const int *__restrict__ tileptr,
+                       const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
+                       const int4 *__restrict__ arow, int *__restrict__ counts)
+{
+    extern __shared__ unsigned sm_u[];
+    __shared__ int red[32];
+    unsigned *bm = sm_u;
+    const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x)
+    {
+        const int row = rows[r];
+        const int4 info = arow[row];
+        const int tbase = info.z >> MHB_TILE_SHIFT;
+        const int wt = (info.w >> MHB_TILE_SHIFT) - tbase + 1;
+        for (int w = threadIdx.x; w < wt; w += blockDim.x)
+            bm[w] = 0u;
+        __syncthreads();
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        // each warp takes 32 entries of A's row at a time; lanes fetch the tile ranges
+        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
+        {
+            int ts = 0, te = 0;
+            if (j0 + lane < e)
+            {
+                int k = __ldg(&Ac[j0 + lane]);
+                ts = __ldg(&tileptr[k]);
+                te = __ldg(&tileptr[k + 1]);
+            }
+            const int cnt = min(32, e - j0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                const int qs = __shfl_sync(kFull, ts, i), qe = __shfl_sync(kFull, te, i);
+                for (int q = qs + lane; q < qe; q += 32)
+                    atomicOr(&bm[__ldg(&tilecol[q]) - tbase], __ldg(&tilemask[q]));
+            }
+        }
+        __syncthreads();
+        int c = 0;
+        for (int w = threadIdx.x; w < wt; w += blockDim.x)
+            c += __popc(bm[w]);
+        c = block_sum_int(c, red);
+        if (threadIdx.x == 0)
+            counts[row] = c;
+        __syncthreads();
+    }
+}
+
+// ---- tile hash: insert (tilecol -> OR mask) with linear probing -------------------------
+template <bool ATOMIC_OR>
+__device__ __forceinline__ void tile_insert(int *keys, unsigned *masks, int logS, int tc, unsigned m, int *scal)
+{
+    const unsigned S1 = (1u << logS) - 1u;
+    unsigned h = hash_slot((unsigned)tc, logS);
+    for (unsigned it = 0; it <= S1; ++it)
+    {
+        int old = keys[h];
+        if (old != tc)
+        {
+            if (old != -1)
+            {
+                h = (h + 1) & S1;
+                continue;
+            }
+            old = atomicCAS(&keys[h], -1, tc);
+            if (old != -1 && old != tc)
+            {
+                h = (h + 1) & S1;
+                continue;
+            }
+        }
+        if (ATOMIC_OR)
+            atomicOr(&masks[h], m);
+        else
+            masks[h] |= m;
+        return;
+    }
+    atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kSymThreads)
+    k_sym_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                     const int *__restrict__ Ac, const int *__restrict__ tileptr,
+                     const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
+                     int *__restrict__ counts, int logS, int *__restrict__ scal)
+{
+    extern __shared__ unsigned sm_u[];
+    constexpr int GPB = kSymThreads / G;
+    const int g = threadIdx.x / G, l = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const int S = 1 << logS;
+    int *keys = (int *)sm_u + (size_t)g * 2 * S;
+    unsigned *masks = (unsigned *)(keys + S);
+    for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
+    {
+        const int row = rows[r];
+        for (int w = l; w < S; w += G)
+        {
+            keys[w] = -1;
+            masks[w] = 0u;
+        }
+        __syncwarp(gm);
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        for (int j0 = s; j0 < e; j0 += G)
+        {
+            int ts = 0, te = 0;
+            if (j0 + l < e)
+            {
+                int k = __ldg(&Ac[j0 + l]);
+                ts = __ldg(&tileptr[k]);
+                te = __ldg(&tileptr[k + 1]);
+            }
+            const int cnt = min(G, e - j0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                const int qs = __shfl_sync(gm, ts, i, G), qe = __shfl_sync(gm, te, i, G);
+                for (int q = qs + l; q < qe; q += G)
+                    tile_insert<false>(keys, masks, logS, __ldg(&tilecol[q]), __ldg(&tilemask[q]), scal);
+                __syncwarp(gm);
+            }
+        }
+        int c = 0;
+        for (int w = l; w < S; w += G)
+            c += __popc(masks[w]);
+        c = group_sum<G>(c, gm);
+        if (l == 0)
+            counts[row] = c;
+        __syncwarp(gm);
+    }
+}
+
+// One block per row; table in shared memory (pool == nullptr) or in a per-block slice of
+// the global pool (2 * pool_slots ints per block), sized per row from its tile upper bound.
+__global__ void __launch_bounds__(kSymThreads)
+    k_sym_hash_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                     const int *__restrict__ Ac, const int *__restrict__ tileptr,
+                     const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
+                     const int4 *__restrict__ arow, int *__restrict__ counts, int logS_fixed,
+                     int *__restrict__ pool, long long pool_slots, int *__restrict__ scal)
+{
+    extern __shared__ unsigned sm_u[];
+    __shared__ int red[32];
+    const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x)
+    {
+        const int row = rows[r];
+        int logS = logS_fixed;
+        int *keys;
+        if (pool)
+        {
+            // per-row size: next power of two >= 1.5 * min(tile-flop, spanned words)
+            const int4 info = arow[row];
+            long long wt = (long long)(info.w >> MHB_TILE_SHIFT) - (info.z >> MHB_TILE_SHIFT) + 1;
+            long long ub = wt < info.y ? wt : info.y;
+            logS = 10;
+            while ((1LL << logS) < ub + (ub >> 1) + 1)
+                ++logS;
+            keys = pool + (size_t)blockIdx.x * 2 * pool_slots;
+        }
+        else
+            keys = (int *)sm_u;
+        const int S = 1 << logS;
+        unsigned *masks = (unsigned *)(keys + S);
+        for (int w = threadIdx.x; w < S; w += blockDim.x)
+        {
+            keys[w] = -1;
+            masks[w] = 0u;
+        }
+        __syncthreads();
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
+        {
+            int ts = 0, te = 0;
+            if (j0 + lane < e)
+            {
+                int k = __ldg(&Ac[j0 + lane]);
+                ts = __ldg(&tileptr[k]);
+                te = __ldg(&tileptr[k + 1]);
+            }
+            const int cnt = min(32, e - j0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                const int qs = __shfl_sync(kFull, ts, i), qe = __shfl_sync(kFull, te, i);
+                for (int q = qs + lane; q < qe; q += 32)
+                    tile_insert<true>(keys, masks, logS, __ldg(&tilecol[q]), __ldg(&tilemask[q]), scal);
+            }
+        }
+        __syncthreads();
+        int c = 0;
+        for (int w = threadIdx.x; w < S; w += blockDim.x)
+            c += __popc(pool ? __ldcg(&masks[w]) : masks[w]); // pool: read at L2, where the atomics landed
+        c = block_sum_int(c, red);
+        if (threadIdx.x == 0)
+            counts[row] = c;
+        __syncthreads();
+    }
+}
+
+} // namespace mhb

@@ -1,0 +1,145 @@
+"""GPU bring-up: stage-by-stage parity of the CUDA path against the oracle (and the
+reference kernels when oracle/_ref is present), with verbose diagnostics.  Not a test --
+tests/ holds the real parity suite; this prints as much as possible before failing."""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mh_spgemm_b200  # noqa: E402
+from mh_spgemm_b200 import api, generators as G  # noqa: E402
+from mh_spgemm_b200.csr import CSR  # noqa: E402
+from oracle import Oracle, Reference  # noqa: E402
+
+orc = Oracle()
+tool = api.Tool(0)
+FAILS = []
+
+
+def check(name, A, B=None, force=(0, 0), ref=None, time_it=False):
+    B = A if B is None else B
+    tool.set_option("force_sym_path", force[0])
+    tool.set_option("force_num_path", force[1])
+    tag = f"{name} force={force}"
+    t0 = time.time()
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    t_orc = time.time() - t0
+    # family 1
+    dBp, dBc = api.DeviceArray(B.ptr), api.DeviceArray(B.col)
+    tp, tc, tm = tool.mask_matrix_B(B.M, B.N, dBp, dBc)
+    otp, otc, otm = orc.mask_matrix(B)
+    ok1 = np.array_equal(tp, otp) and np.array_equal(tc, otc) and np.array_equal(tm, otm)
+    # full spgemm through the host API
+    try:
+        C = tool.spgemm_host(A, B)
+    except Exception as e:  # noqa: BLE001
+        print(f"[FAIL] {tag}: {e}")
+        FAILS.append(tag)
+        return
+    st = tool.stats
+    tmg = tool.timing
+    ok_ptr = np.array_equal(C.ptr.astype(np.int64), Cp)
+    ok_col = ok_ptr and np.array_equal(C.col, Cc)
+    tol = 1e-12 if A.val.dtype == np.float64 else 1e-5
+    ok_val = False
+    err = float("nan")
+    if ok_col:
+        denom = np.maximum(np.abs(Cv), np.abs(C.val))
+        denom[denom == 0] = 1
+        err = float((np.abs(C.val - Cv) / denom).max()) if Cv.size else 0.0
+        ok_val = err <= tol
+    ok_ip = st["intprod"] == orc.intprod(A, B)
+    status = "ok" if (ok1 and ok_ptr and ok_col and ok_val and ok_ip) else "FAIL"
+    print(f"[{status}] {tag}: M={A.M} nnzA={A.nnz} nnzC={Cp[-1]} mask={ok1} ptr={ok_ptr} col={ok_col} "
+          f"val={ok_val} (err {err:.2e}) intprod={ok_ip} | total {tmg.total:.3f} ms "
+          f"(mask {tmg.Form_mask_matrix_B:.3f} symbin {tmg.symbolic_binning:.3f} sym {tmg.Calculate_C_nnz:.3f} "
+          f"numbin {tmg.numeric_binning:.3f} handoff {tmg.Malloc_C_col_val:.3f} num {tmg.Numeric:.3f}) "
+          f"launches {st['gpu_launches']} oracle {t_orc*1e3:.0f} ms")
+    print("       sym bins", {k: v for k, v in st["sym_bins"].items() if v}, "num bins",
+          {k: v for k, v in st["num_bins"].items() if v})
+    if status != "ok":
+        FAILS.append(tag)
+        if not ok_ptr:
+            got = np.diff(C.ptr.astype(np.int64))
+            exp = np.diff(Cp)
+            bad = np.nonzero(got != exp)[0]
+            info = tool.row_info(A.M)
+            nb, bins, off = tool.bins(0, A.M)
+            binof = np.zeros(A.M, np.int32)
+            for b in range(nb):
+                binof[bins[off[b]:off[b + 1]]] = b
+            print("       first bad rows:", [(int(r), int(got[r]), int(exp[r]), api.SYM_BINS[binof[r]],
+                                              info[r].tolist()) for r in bad[:8]], "nbad", bad.size)
+        elif not ok_col or not ok_val:
+            nb, bins, off = tool.bins(1, A.M)
+            binof = np.zeros(A.M, np.int32)
+            for b in range(nb):
+                binof[bins[off[b]:off[b + 1]]] = b
+            badj = np.nonzero((C.col != Cc) | ~(np.abs(C.val - Cv) <= tol * np.maximum(np.abs(Cv), 1e-300)))[0]
+            rows = np.searchsorted(Cp, badj[:2000], side="right") - 1
+            ur = np.unique(rows)
+            print("       bad rows:", [(int(r), api.NUM_BINS[binof[r]], int(Cp[r + 1] - Cp[r])) for r in ur[:8]],
+                  "nbad entries", badj.size)
+            r = int(ur[0])
+            print("       row", r, "got cols", C.col[Cp[r]:Cp[r + 1]][:16], "exp", Cc[Cp[r]:Cp[r + 1]][:16])
+            print("       got vals", C.val[Cp[r]:Cp[r + 1]][:6], "exp", Cv[Cp[r]:Cp[r + 1]][:6])
+    if ref is not None and A.val.dtype == np.float64:
+        try:
+            R = ref.spgemm(A, B, reps=3, warmup=1, e2e_reps=2, want_mask=True)
+            okr = np.array_equal(R["ptr"].astype(np.int64), Cp) and np.array_equal(R["col"], Cc)
+            rerr = float((np.abs(R["val"] - Cv) / np.maximum(np.abs(Cv), 1e-300)).max()) if Cv.size else 0.0
+            print(f"       reference: structure==oracle {okr} val err {rerr:.2e} device {R['ms_device']:.3f} ms "
+                  f"e2e {R['ms_e2e']:.3f} ms stages {np.round(R['stage_ms'], 3).tolist()}")
+            if not okr:
+                FAILS.append(tag + " (reference vs oracle)")
+        except Exception as e:  # noqa: BLE001
+            print("       reference failed:", e)
+    if time_it:
+        PA = tool.pin(A)
+        ts, te = [], []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            tool.spgemm_host(PA, PA if B is A else tool.pin(B), copy=False)
+            te.append((time.perf_counter() - t0) * 1e3)
+            ts.append(tool.timing.total)
+        ip = st["intprod"]
+        print(f"       steady: device total {np.median(ts):.3f} ms -> {2*ip/np.median(ts)/1e6:.1f} GFLOPS ; "
+              f"e2e host {np.median(te):.3f} ms -> {2*ip/np.median(te)/1e6:.1f} GFLOPS")
+
+
+def main():
+    ref = None
+    if Reference.available() and "--noref" not in sys.argv:
+        try:
+            ref = Reference()
+        except Exception as e:  # noqa: BLE001
+            print("reference unavailable:", e)
+    rng_cases = [
+        ("tiny-uniform", G.uniform_random(64, 64, 300, seed=1)),
+        ("rect-uniform", (G.uniform_random(200, 300, 2000, seed=2), G.uniform_random(300, 5000, 9000, seed=3))),
+        ("poisson-32", G.poisson2d(32)),
+        ("fem-small", G.fem3d(4, 4, 10, 3, seed=5)),
+        ("rmat-14", G.rmat(14, 16000, 60000, seed=6)),
+        ("dense-rows", G.with_dense_rows(G.uniform_random(3000, 3000, 30000, seed=8), 6, 1500, seed=9)),
+        ("empty", CSR(5, 5, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0))),
+    ]
+    for name, a in rng_cases:
+        A, B = a if isinstance(a, tuple) else (a, None)
+        for force in ((0, 0), (1, 1), (2, 2)):
+            check(name, A, B, force)
+    check("poisson-32 f32", G.poisson2d(32, dtype=np.float32))
+    check("fem-small f32", G.fem3d(4, 4, 10, 3, seed=5, dtype=np.float32))
+    if "--small" not in sys.argv:
+        check("P", G.poisson2d(256), ref=ref, time_it=True)
+        check("F", G.fem3d(), ref=ref, time_it=True)
+        check("R", G.rmat(), ref=ref, time_it=True)
+    print("FAILS:", FAILS)
+    return 1 if FAILS else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
