@@ -127,14 +127,17 @@ def main():
         ("dense-rows", G.with_dense_rows(G.uniform_random(3000, 3000, 30000, seed=8), 6, 1500, seed=9)),
         ("empty", CSR(5, 5, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0))),
     ]
-    for name, a in rng_cases:
-        A, B = a if isinstance(a, tuple) else (a, None)
-        for force in ((0, 0), (1, 1), (2, 2)):
-            check(name, A, B, force)
-    check("poisson-32 f32", G.poisson2d(32, dtype=np.float32))
-    check("fem-small f32", G.fem3d(4, 4, 10, 3, seed=5, dtype=np.float32))
+    if "--big" not in sys.argv:
+        for name, a in rng_cases:
+            A, B = a if isinstance(a, tuple) else (a, None)
+            for force in ((0, 0), (1, 1), (2, 2)):
+                check(name, A, B, force)
+        check("poisson-32 f32", G.poisson2d(32, dtype=np.float32))
+        check("fem-small f32", G.fem3d(4, 4, 10, 3, seed=5, dtype=np.float32))
     if "--small" not in sys.argv:
-        check("P", G.poisson2d(256), ref=ref, time_it=True)
+        # the reference itself faults on Poisson (all C rows <= 22 nnz: its empty-grid
+        # k_init_group_size launch leaves an error that makes the CUB scan bail out)
+        check("P", G.poisson2d(256), ref=None, time_it=True)
         check("F", G.fem3d(), ref=ref, time_it=True)
         check("R", G.rmat(), ref=ref, time_it=True)
     print("FAILS:", FAILS)

@@ -1,0 +1,235 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the oracle on seeded inputs, against the committed reference fixtures, and --
+at BASELINE.json's full sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): row_ptr and col_idx bit-exact; values 1e-12
+relative for fp64 and 1e-5 for fp32 (accumulation order differs from the oracle's)."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import mh_spgemm_b200  # noqa: F401
+from mh_spgemm_b200 import api, generators as G
+from mh_spgemm_b200.csr import CSR
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+def sha(a, dt):
+    return hashlib.sha256(np.ascontiguousarray(a, dt).tobytes()).hexdigest()
+
+
+def assert_matches(orc, C, Cp, Cc, Cv):
+    assert np.array_equal(C.ptr.astype(np.int64), Cp), "row_ptr differs"
+    assert np.array_equal(C.col, Cc), "col_idx differs"
+    bad, first = orc.compare(C.M, (C.ptr, C.col, C.val), (Cp, Cc, Cv), RTOL[C.val.dtype])
+    assert bad == 0, f"{bad} values out of tolerance, first at {first}"
+
+
+INPUTS = {
+    "tiny": lambda: (G.uniform_random(64, 64, 300, seed=1), None),
+    "rect": lambda: (G.uniform_random(200, 300, 2000, seed=2), G.uniform_random(300, 5000, 9000, seed=3)),
+    "poisson32": lambda: (G.poisson2d(32), None),
+    "fem": lambda: (G.fem3d(4, 4, 10, 3, seed=5), None),
+    "rmat14": lambda: (G.rmat(14, 16000, 60000, seed=6), None),
+    "dense_rows": lambda: (G.with_dense_rows(G.uniform_random(3000, 3000, 30000, seed=8), 6, 1500, seed=9), None),
+    "banded": lambda: (G.banded_random(5000, 12, 300, seed=10), None),
+    "road": lambda: (G.road_grid(60), None),
+    "one_row": lambda: (CSR(1, 1, [0, 1], [0], [2.0]), None),
+    "empty": lambda: (CSR(5, 5, np.zeros(6, np.int32), [], []), None),
+    "ragged": lambda: (CSR(3, 3, [0, 0, 3, 3], [0, 1, 2], [1.0, 2.0, 3.0]), None),
+}
+
+
+@pytest.mark.parametrize("force", [(0, 0), (1, 1), (2, 2), (1, 2), (2, 1)])
+@pytest.mark.parametrize("name", list(INPUTS))
+def test_spgemm_matches_oracle(tool, orc, name, force):
+    """Every accumulator path (auto / dense bitmap+window / hash) gives the same CSR."""
+    A, B = INPUTS[name]()
+    B = A if B is None else B
+    tool.set_option("force_sym_path", force[0])
+    tool.set_option("force_num_path", force[1])
+    try:
+        C = tool.spgemm_host(A, B)
+    finally:
+        tool.set_option("force_sym_path", 0)
+        tool.set_option("force_num_path", 0)
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    assert_matches(orc, C, Cp, Cc, Cv)
+    assert tool.stats["intprod"] == orc.intprod(A, B)
+    assert tool.stats["gpu_launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["poisson32", "fem", "rmat14", "dense_rows"])
+def test_fp32(tool, orc, name):
+    A, B = INPUTS[name]()
+    A = A.astype(np.float32)
+    C = tool.spgemm_host(A, A)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    assert C.val.dtype == np.float32
+    assert_matches(orc, C, Cp, Cc, Cv)
+
+
+def test_poisson_is_exact(tool, orc):
+    """BASELINE configs[0]: Poisson 256^2, A*A is exact in fp64 -> values bit-for-bit."""
+    A = G.poisson2d(256)
+    C = tool.spgemm_host(A, A)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    assert C.nnz == 846852
+    assert np.array_equal(C.ptr.astype(np.int64), Cp) and np.array_equal(C.col, Cc)
+    assert np.array_equal(C.val, Cv)
+
+
+@pytest.mark.parametrize("name", list(cases.SMALL))
+def test_matches_reference_fixture_full(tool, name):
+    """Bit-exact structure against what the reference's own kernels produced on a B200."""
+    A, B = cases.SMALL[name]()
+    B = A if B is None else B
+    ref = np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+    C = tool.spgemm_host(A, B)
+    assert np.array_equal(C.ptr, ref["ptr"]) and np.array_equal(C.col, ref["col"])
+    np.testing.assert_allclose(C.val, ref["val"], rtol=1e-12, atol=0)
+    # family 1 against the reference's mask matrix
+    tp, tc, tm = tool.mask_matrix_B(B.M, B.N, api.DeviceArray(B.ptr), api.DeviceArray(B.col))
+    assert np.array_equal(tp, ref["tileptr"]) and np.array_equal(tc, ref["tilecol"])
+    assert np.array_equal(tm, ref["tilemask"])
+
+
+@pytest.mark.parametrize("name", ["dense_rows", "rmat_s14", "fem_small", "F_cant_like", "R_webbase_like"])
+def test_matches_reference_fixture_checksums(tool, name):
+    """Full-size BASELINE configs[1] and [2] against checksums of the reference's output."""
+    A, B = cases.LARGE[name]()
+    B = A if B is None else B
+    meta = json.load(open(os.path.join(GOLD, f"ref_{name}.json")))
+    C = tool.spgemm_host(A, B)
+    assert C.nnz == meta["nnz"]
+    assert sha(C.ptr, np.int32) == meta["sha_ptr"]
+    assert sha(C.col, np.int32) == meta["sha_col"]
+    assert float(C.val.sum()) == pytest.approx(meta["sum_val"], rel=1e-10)
+    w = (np.arange(C.val.size, dtype=np.int64) % 97 + 1).astype(np.float64)
+    assert float((C.val * w).sum()) == pytest.approx(meta["sum_weighted"], rel=1e-10)
+    tp, tc, tm = tool.mask_matrix_B(B.M, B.N, api.DeviceArray(B.ptr), api.DeviceArray(B.col))
+    assert sha(tp, np.int32) == meta["sha_tileptr"]
+    assert sha(tc, np.int32) == meta["sha_tilecol"]
+    assert sha(tm, np.uint32) == meta["sha_tilemask"]
+
+
+def test_live_reference_same_box():
+    """C's structure bit-exact against the reference's own GPU implementation run here, now
+    (separate process: a fault in the reference must not take the test session down)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libmhref.so")):
+        pytest.skip("oracle/_ref not built")
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import mh_spgemm_b200\n"
+        "from mh_spgemm_b200 import api, generators as G; from oracle import Reference\n"
+        "A = G.fem3d(6, 6, 20, 3, seed=77)\n"
+        "C = api.Tool(0).spgemm_host(A, A); R = Reference().spgemm(A, A)\n"
+        "assert np.array_equal(C.ptr, R['ptr']) and np.array_equal(C.col, R['col'])\n"
+        "np.testing.assert_allclose(C.val, R['val'], rtol=1e-12, atol=0); print('LIVE-OK', C.nnz)\n" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "LIVE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_stage_outputs(tool, orc):
+    """Families 1 and 2 stage by stage: mask matrix, per-row products / tile-flop / column
+    span, and the bins (a stable partition of the rows that agrees with the ladder)."""
+    A = G.rmat(13, 8000, 40000, seed=12)
+    dAp, dAc = api.DeviceArray(A.ptr), api.DeviceArray(A.col)
+    tp, tc, tm = tool.mask_matrix_B(A.M, A.N, dAp, dAc)
+    otp, otc, otm = orc.mask_matrix(A)
+    assert np.array_equal(tp, otp) and np.array_equal(tc, otc) and np.array_equal(tm, otm)
+    dCp, nnzC = tool.symbolic(A.M, A.N, A.N, dAp, dAc, dAp, dAc)
+    Cp = orc.symbolic(A, A)
+    assert nnzC == Cp[-1] and np.array_equal(dCp.numpy().astype(np.int64), Cp)
+    info = tool.row_info(A.M)
+    ip = orc.row_intprod(A, A)
+    assert np.array_equal(info[:, 0], ip)
+    assert np.array_equal(info[:, 1], orc.row_tileflop(A, otp))
+    # column span of every non-empty C row
+    nz = np.diff(Cp) > 0
+    _, Cc, _ = orc.spgemm(A, A)
+    first = Cc[Cp[:-1][nz]]
+    last = Cc[Cp[1:][nz] - 1]
+    assert np.array_equal(info[nz, 2], first) and np.array_equal(info[nz, 3], last)
+    for which, key in ((0, "sym_bins"), (1, "num_bins")):
+        nb, bins, off = tool.bins(which, A.M)
+        assert off[0] == 0 and off[nb] == A.M
+        assert np.array_equal(np.sort(bins), np.arange(A.M)), "bins must be a permutation of the rows"
+        for b in range(nb):
+            seg = bins[off[b]:off[b + 1]]
+            assert np.all(np.diff(seg) > 0), "row ids ascending inside a bin (stable partition)"
+        assert np.array_equal(np.diff(off[:nb + 1]), list(tool.stats[key].values())[:nb])
+    nb, bins, off = tool.bins(1, A.M)
+    assert np.array_equal(np.sort(bins[off[0]:off[1]]), np.nonzero(~nz)[0]), "bin 0 == empty C rows"
+
+
+def test_symbolic_numeric_contract(tool, orc):
+    """Two separately callable phases; numeric re-runnable with new values on one pattern."""
+    A = G.fem3d(5, 5, 12, 3, seed=21)
+    dAp, dAc, dAv = api.DeviceArray(A.ptr), api.DeviceArray(A.col), api.DeviceArray(A.val)
+    dCp, nnzC = tool.symbolic(A.M, A.N, A.N, dAp, dAc, dAp, dAc)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    assert nnzC == Cp[-1]
+    dCc, dCv = tool.numeric(dAv, dAv, nnzC)
+    assert np.array_equal(dCc.numpy()[:nnzC], Cc)
+    np.testing.assert_allclose(dCv.numpy()[:nnzC], Cv, rtol=1e-12, atol=0)
+    A2 = CSR(A.M, A.N, A.ptr, A.col, A.val * 3.0 - 1.0)
+    dAv2 = api.DeviceArray(A2.val)
+    dCc2, dCv2 = tool.numeric(dAv2, dAv2, nnzC)
+    _, Cc2, Cv2 = orc.spgemm(A2, A2)
+    assert np.array_equal(dCc2.numpy()[:nnzC], Cc2)
+    bad, _ = orc.compare(A.M, (Cp, Cc2, dCv2.numpy()[:nnzC]), (Cp, Cc2, Cv2), 1e-12)
+    assert bad == 0
+
+
+def test_numeric_before_symbolic_is_an_error():
+    t = api.Tool(0)
+    d = api.DeviceArray(np.zeros(4))
+    with pytest.raises(api.MhbError):
+        t.numeric_into(d, d, d, d)
+    t.release()
+
+
+def test_special_values_stay_structural(tool, orc):
+    """Cancellation to 0.0, NaN and Inf products remain stored entries (no value test on the
+    accumulate path, inc/numeric.cuh:237-241); the window's 'unset' marker never collides."""
+    A = CSR(3, 3, [0, 2, 3, 4], [0, 1, 1, 2], [1.0, -1.0, np.inf, np.nan])
+    B = CSR(3, 3, [0, 1, 2, 3], [0, 0, 2], [1.0, 1.0, 0.0])
+    for force in (1, 2):
+        tool.set_option("force_num_path", force)
+        C = tool.spgemm_host(A, B)
+        tool.set_option("force_num_path", 0)
+        assert C.ptr.tolist() == [0, 1, 2, 3] and C.col.tolist() == [0, 0, 2]
+        assert C.val[0] == 0.0 and np.isinf(C.val[1]) and np.isnan(C.val[2])
+
+
+def test_full_size_properties(tool):
+    """Size-independent properties at BASELINE's full sizes (no oracle needed): sorted and
+    duplicate-free rows, row sums equal A*(B*1) (linearity), pattern symmetric for a
+    symmetric-pattern input, and idempotence of a repeated call."""
+    for A in (G.fem3d(), G.rmat()):
+        C = tool.spgemm_host(A, A)
+        assert C.is_canonical()
+        S = A.to_scipy()
+        want = S @ (S @ np.ones(A.N))
+        got = np.add.reduceat(np.append(C.val, 0.0), np.minimum(C.ptr[:-1], C.nnz))
+        got[np.diff(C.ptr) == 0] = 0.0
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-9)
+        C2 = tool.spgemm_host(A, A)
+        assert np.array_equal(C.ptr, C2.ptr) and np.array_equal(C.col, C2.col)
+        np.testing.assert_allclose(C.val, C2.val, rtol=1e-12, atol=0)
+    # FEM pattern is symmetric -> so is the pattern of A*A
+    A = G.fem3d(6, 6, 30, 3, seed=9)
+    C = tool.spgemm_host(A, A)
+    P = C.to_scipy()
+    P.data[:] = 1
+    assert (P != P.T).nnz == 0
