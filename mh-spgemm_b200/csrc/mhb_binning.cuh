@@ -191,78 +191,94 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
                                                       int *__restrict__ scal, int force_path)
 {
     constexpr int kLong = 32 * G; // rows longer than this are walked by the whole warp
+    constexpr int GPW = 32 / G;   // rows per warp and step
+    __shared__ long long sh_ip[8], sh_tf[8];
+    __shared__ int sh_mx[8];
     const int l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
-    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool valid = gid < M;
-    const int row = valid ? (int)gid : 0;
-    int s = 0, e = 0;
-    if (valid)
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long ip_tot = 0, tf_tot = 0;
+    int tf_max = 0;
+    // persistent grid: the trip count is warp-uniform so the ballots below are convergent
+    for (long long base = warp0 * GPW; base < M; base += nwarps * GPW)
     {
-        s = __ldg(&Ap[row]);
-        e = __ldg(&Ap[row + 1]);
-    }
-    RowAcc a{0, 0, INT_MAX, -1};
-    const bool is_long = (e - s) > kLong;
-    if (!is_long)
-        row_acc_range(a, Ac, binfo, s, e, l, G);
-    if (G < 32)
-    {
+        const long long gid = base + lane_id() / G;
+        const bool valid = gid < M;
+        const int row = valid ? (int)gid : 0;
+        int s = 0, e = 0;
+        if (valid)
+        {
+            s = __ldg(&Ap[row]);
+            e = __ldg(&Ap[row + 1]);
+        }
+        RowAcc a{0, 0, INT_MAX, -1};
+        const bool is_long = (G < 32) && (e - s) > kLong;
+        if (!is_long)
+            row_acc_range(a, Ac, binfo, s, e, l, G);
         a.ip = group_sum<G>(a.ip, gm);
         a.tf = group_sum<G>(a.tf, gm);
         a.cmin = group_min<G>(a.cmin, gm);
         a.cmax = group_max<G>(a.cmax, gm);
-        // long rows: every lane of the warp helps, one row at a time
-        unsigned todo = __ballot_sync(kFull, is_long && l == 0);
-        while (todo)
+        if (G < 32)
         {
-            int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            int rs = __shfl_sync(kFull, s, src), re = __shfl_sync(kFull, e, src);
-            RowAcc w{0, 0, INT_MAX, -1};
-            row_acc_range(w, Ac, binfo, rs, re, lane_id(), 32);
-            w.ip = group_sum<32>(w.ip, kFull);
-            w.tf = group_sum<32>(w.tf, kFull);
-            w.cmin = group_min<32>(w.cmin, kFull);
-            w.cmax = group_max<32>(w.cmax, kFull);
-            if ((lane_id() & ~(G - 1)) == src)
-                a = w;
+            // long rows: every lane of the warp helps, one row at a time
+            unsigned todo = __ballot_sync(kFull, is_long && l == 0);
+            while (todo)
+            {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int rs = __shfl_sync(kFull, s, src), re = __shfl_sync(kFull, e, src);
+                RowAcc w{0, 0, INT_MAX, -1};
+                row_acc_range(w, Ac, binfo, rs, re, lane_id(), 32);
+                w.ip = group_sum<32>(w.ip, kFull);
+                w.tf = group_sum<32>(w.tf, kFull);
+                w.cmin = group_min<32>(w.cmin, kFull);
+                w.cmax = group_max<32>(w.cmax, kFull);
+                if ((lane_id() & ~(G - 1)) == src)
+                    a = w;
+            }
+        }
+        if (valid && l == 0)
+        {
+            const int ip = sat_i32(a.ip), tf = sat_i32(a.tf);
+            arow[row] = make_int4(ip, tf, a.cmin, a.cmax);
+            const int b = mhb_classify_sym(ip, tf, a.cmin, a.cmax, force_path);
+            binid[row] = (unsigned char)b;
+            if (b == SB_EMPTY)
+                counts[row] = 0;
+            if (row == 0)
+                counts[M] = 0;
+            ip_tot += a.ip;
+            tf_tot += a.tf;
+            tf_max = max(tf_max, tf);
         }
     }
-    else
-    {
-        if (is_long)
-            row_acc_range(a, Ac, binfo, s, e, l, 32);
-        a.ip = group_sum<32>(a.ip, kFull);
-        a.tf = group_sum<32>(a.tf, kFull);
-        a.cmin = group_min<32>(a.cmin, kFull);
-        a.cmax = group_max<32>(a.cmax, kFull);
-    }
-    long long ip_tot = 0, tf_tot = 0;
-    int tf_max = 0;
-    if (valid && l == 0)
-    {
-        int ip = sat_i32(a.ip), tf = sat_i32(a.tf);
-        arow[row] = make_int4(ip, tf, a.cmin, a.cmax);
-        int b = mhb_classify_sym(ip, tf, a.cmin, a.cmax, force_path);
-        binid[row] = (unsigned char)b;
-        if (b == SB_EMPTY)
-            counts[row] = 0;
-        if (row == 0)
-            counts[M] = 0;
-        ip_tot = a.ip;
-        tf_tot = a.tf;
-        tf_max = tf;
-    }
-    // one atomic per warp for the totals
+    // one set of atomics per block (per-warp atomics on three hot addresses serialise in L2)
     ip_tot = group_sum<32>(ip_tot, kFull);
     tf_tot = group_sum<32>(tf_tot, kFull);
     tf_max = group_max<32>(tf_max, kFull);
-    if (lane_id() == 0 && (ip_tot | tf_tot))
+    if (lane_id() == 0)
     {
-        atomicAdd((unsigned long long *)(scal + SC_INTPROD_LO), (unsigned long long)ip_tot);
-        atomicAdd((unsigned long long *)(scal + SC_TILEFLOP_LO), (unsigned long long)tf_tot);
-        atomicMax(scal + SC_MAX_TILEFLOP, tf_max);
+        sh_ip[threadIdx.x >> 5] = ip_tot;
+        sh_tf[threadIdx.x >> 5] = tf_tot;
+        sh_mx[threadIdx.x >> 5] = tf_max;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        {
+            ip_tot += sh_ip[w];
+            tf_tot += sh_tf[w];
+            tf_max = max(tf_max, sh_mx[w]);
+        }
+        if (ip_tot | tf_tot)
+        {
+            atomicAdd((unsigned long long *)(scal + SC_INTPROD_LO), (unsigned long long)ip_tot);
+            atomicAdd((unsigned long long *)(scal + SC_TILEFLOP_LO), (unsigned long long)tf_tot);
+            atomicMax(scal + SC_MAX_TILEFLOP, tf_max);
+        }
     }
 }
 
@@ -280,9 +296,18 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
         int4 info = arow[i];
         binid[i] = (unsigned char)mhb_classify_num(n, info.z, info.w, force_path);
     }
+    __shared__ int sh_mx[8];
     n = group_max<32>(n, kFull);
-    if (lane_id() == 0 && n > 0)
-        atomicMax(scal + SC_MAX_ROWNNZ, n);
+    if (lane_id() == 0)
+        sh_mx[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            n = max(n, sh_mx[w]);
+        if (n > 0)
+            atomicMax(scal + SC_MAX_ROWNNZ, n);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -507,10 +507,10 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     {
         double avg = (double)nnzA / M;
         if (avg > 12.0)
-            LAUNCH(h, k_arow_metrics<32>, cdiv((long long)M * 32, 256), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
+            LAUNCH(h, k_arow_metrics<32>, std::min(cdiv((long long)M * 32, 256), h->num_sms * 16), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
                    h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
         else
-            LAUNCH(h, k_arow_metrics<4>, cdiv((long long)M * 4, 256), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
+            LAUNCH(h, k_arow_metrics<4>, std::min(cdiv((long long)M * 4, 256), h->num_sms * 16), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
                    h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
     }
     else

@@ -22,11 +22,14 @@
 // rows) fall back to atomicAdd.  Loads of B are coalesced along the B row.
 #pragma once
 #include "mhb_common.cuh"
+#include "mhb_stream.cuh"
 
 namespace mhb
 {
 
 constexpr int kNumGroupThreads = 256;
+constexpr int kNumDepth = 4; // items (chunks of B) in flight per group, see mhb_stream.cuh
+constexpr int kPre = 3;      // chunks of the next B row prefetched by the dense-window kernel
 
 // =========================================================================================
 // Dense window, G lanes per row.
@@ -53,40 +56,76 @@ __global__ void __launch_bounds__(kNumGroupThreads)
             acc[i] = Unset<T>::value();
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        // Walk A's row 32 (G) nonzeros at a time.  The first kPre chunks of the B row of
+        // nonzero i+1 are loaded into registers before nonzero i is accumulated, so the L2
+        // latency of B overlaps the shared-memory updates; the A-side metadata of the next
+        // G nonzeros is prefetched the same way.
+        int bs = 0, be = 0, nbs = 0, nbe = 0;
+        T av = T(0), nav = T(0);
+        auto load_meta = [&](int j, int &ms, int &me, T &ma) {
+            ms = 0, me = 0, ma = T(0);
+            if (j < e)
+            {
+                const int k = __ldg(&Ac[j]);
+                ma = __ldg(&Av[j]);
+                ms = __ldg(&Bp[k]);
+                me = __ldg(&Bp[k + 1]);
+            }
+        };
+        load_meta(s + l, bs, be, av);
         for (int j0 = s; j0 < e; j0 += G)
         {
-            int bs = 0, be = 0;
-            T av = T(0);
-            if (j0 + l < e)
-            {
-                const int k = __ldg(&Ac[j0 + l]);
-                av = __ldg(&Av[j0 + l]);
-                bs = __ldg(&Bp[k]);
-                be = __ldg(&Bp[k + 1]);
-            }
+            load_meta(j0 + G + l, nbs, nbe, nav);
             const int cnt = min(G, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(gm, bs, i, G), qe = __shfl_sync(gm, be, i, G);
-                const T a = __shfl_sync(gm, av, i, G);
-                // two B-row chunks in flight per lane; their columns are distinct
-                for (int q = qs + l; q < qe; q += 2 * G)
+            int pc[kPre], nq = 0, nqe = 0;
+            T pv[kPre], na = T(0);
+            auto issue = [&](int i) {
+                nq = __shfl_sync(gm, bs, i, G);
+                nqe = __shfl_sync(gm, be, i, G);
+                na = __shfl_sync(gm, av, i, G);
+#pragma unroll
+                for (int t = 0; t < kPre; ++t)
                 {
-                    const bool two = q + G < qe;
-                    const int c0 = __ldg(&Bc[q]);
-                    const T v0 = __ldg(&Bv[q]);
-                    const int c1 = two ? __ldg(&Bc[q + G]) : 0;
-                    const T v1 = two ? __ldg(&Bv[q + G]) : T(0);
-                    T o0 = acc[c0 - cmin];
-                    acc[c0 - cmin] = Unset<T>::is(o0) ? a * v0 : fma(a, v0, o0);
-                    if (two)
+                    const int p = nq + t * G + l;
+                    pc[t] = -1;
+                    if (p < nqe)
                     {
-                        T o1 = acc[c1 - cmin];
-                        acc[c1 - cmin] = Unset<T>::is(o1) ? a * v1 : fma(a, v1, o1);
+                        pc[t] = __ldg(&Bc[p]);
+                        pv[t] = __ldg(&Bv[p]);
                     }
                 }
-                __syncwarp(gm);
+            };
+            issue(0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                int cc[kPre];
+                T cv[kPre];
+                const int q = nq, qe = nqe;
+                const T a = na;
+#pragma unroll
+                for (int t = 0; t < kPre; ++t)
+                    cc[t] = pc[t], cv[t] = pv[t];
+                if (i + 1 < cnt)
+                    issue(i + 1);
+                // the columns of one B row are distinct: plain read-modify-write, no atomics
+#pragma unroll
+                for (int t = 0; t < kPre; ++t)
+                    if (cc[t] >= 0)
+                    {
+                        const int idx = cc[t] - cmin;
+                        const T o = acc[idx];
+                        acc[idx] = Unset<T>::is(o) ? a * cv[t] : fma(a, cv[t], o);
+                    }
+                for (int p = q + kPre * G + l; p < qe; p += G) // rows longer than kPre*G
+                {
+                    const int idx = __ldg(&Bc[p]) - cmin;
+                    const T v = __ldg(&Bv[p]);
+                    const T o = acc[idx];
+                    acc[idx] = Unset<T>::is(o) ? a * v : fma(a, v, o);
+                }
+                __syncwarp(gm); // order this B row's stores before the next row's loads
             }
+            bs = nbs, be = nbe, av = nav;
         }
         // ordered compaction: the window is already sorted by column
         int out = __ldg(&Cp[row]);
@@ -305,33 +344,31 @@ __global__ void __launch_bounds__(kNumGroupThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s; j0 < e; j0 += G)
+        ItemStream<G, T, T> st{Ac, Av, Bp, Bc, Bv, gm, l};
+        st.init(s, e);
+        int rc[kNumDepth];
+        T rv[kNumDepth], ra[kNumDepth];
+        bool live[kNumDepth];
+#pragma unroll
+        for (int d = 0; d < kNumDepth; ++d)
+            live[d] = st.next(rc[d], rv[d], ra[d]);
+        while (live[0])
         {
-            int bs = 0, be = 0;
-            T av = T(0);
-            if (j0 + l < e)
+#pragma unroll
+            for (int d = 0; d < kNumDepth; ++d)
             {
-                const int k = __ldg(&Ac[j0 + l]);
-                av = __ldg(&Av[j0 + l]);
-                bs = __ldg(&Bp[k]);
-                be = __ldg(&Bp[k + 1]);
-            }
-            const int cnt = min(G, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(gm, bs, i, G), qe = __shfl_sync(gm, be, i, G);
-                const T a = __shfl_sync(gm, av, i, G);
-                for (int q = qs + l; q < qe; q += G)
+                if (!live[d])
+                    break;
+                if (rc[d] >= 0)
                 {
-                    const int c = __ldg(&Bc[q]);
-                    const T v = __ldg(&Bv[q]);
-                    const int h = key_slot(keys, logS, c);
+                    const int h = key_slot(keys, logS, rc[d]);
                     if (h >= 0)
-                        vals[h] = fma(a, v, vals[h]); // columns of one B row are distinct: no atomic
+                        vals[h] = fma(ra[d], rv[d], vals[h]); // columns of one item are distinct: no atomic
                     else
                         atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
                 }
                 __syncwarp(gm);
+                live[d] = st.next(rc[d], rv[d], ra[d]);
             }
         }
         // in-place compaction to the front of the table, G slots per step

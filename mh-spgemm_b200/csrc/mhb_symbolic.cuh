@@ -19,11 +19,13 @@
 // Block kernels (one block per row, warps on different B rows) use atomicOr.
 #pragma once
 #include "mhb_common.cuh"
+#include "mhb_stream.cuh"
 
 namespace mhb
 {
 
 constexpr int kSymThreads = 256;
+constexpr int kSymDepth = 4; // tile chunks in flight per group, see mhb_stream.cuh
 
 // ---- bitmap, G lanes per row -----------------------------------------------------------
 template <int G>
@@ -48,25 +50,26 @@ __global__ void __launch_bounds__(kSymThreads)
             bm[w] = 0u;
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s; j0 < e; j0 += G)
+        ItemStream<G, NoVal, unsigned> st{Ac, nullptr, tileptr, tilecol, tilemask, gm, l};
+        st.init(s, e);
+        int rc[kSymDepth];
+        unsigned rm[kSymDepth];
+        bool live[kSymDepth];
+        NoVal nv;
+#pragma unroll
+        for (int d = 0; d < kSymDepth; ++d)
+            live[d] = st.next(rc[d], rm[d], nv);
+        while (live[0])
         {
-            int ts = 0, te = 0;
-            if (j0 + l < e)
+#pragma unroll
+            for (int d = 0; d < kSymDepth; ++d)
             {
-                int k = __ldg(&Ac[j0 + l]);
-                ts = __ldg(&tileptr[k]);
-                te = __ldg(&tileptr[k + 1]);
-            }
-            const int cnt = min(G, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(gm, ts, i, G), qe = __shfl_sync(gm, te, i, G);
-                for (int q = qs + l; q < qe; q += G)
-                {
-                    const int w = __ldg(&tilecol[q]) - tbase;
-                    bm[w] |= __ldg(&tilemask[q]);
-                }
+                if (!live[d])
+                    break;
+                if (rc[d] >= 0)
+                    bm[rc[d] - tbase] |= rm[d]; // tiles of one B row are distinct: no atomic
                 __syncwarp(gm);
+                live[d] = st.next(rc[d], rm[d], nv);
             }
         }
         int c = 0;
@@ -201,22 +204,26 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s; j0 < e; j0 += G)
+        ItemStream<G, NoVal, unsigned> st{Ac, nullptr, tileptr, tilecol, tilemask, gm, l};
+        st.init(s, e);
+        int rc[kSymDepth];
+        unsigned rm[kSymDepth];
+        bool live[kSymDepth];
+        NoVal nv;
+#pragma unroll
+        for (int d = 0; d < kSymDepth; ++d)
+            live[d] = st.next(rc[d], rm[d], nv);
+        while (live[0])
         {
-            int ts = 0, te = 0;
-            if (j0 + l < e)
+#pragma unroll
+            for (int d = 0; d < kSymDepth; ++d)
             {
-                int k = __ldg(&Ac[j0 + l]);
-                ts = __ldg(&tileptr[k]);
-                te = __ldg(&tileptr[k + 1]);
-            }
-            const int cnt = min(G, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(gm, ts, i, G), qe = __shfl_sync(gm, te, i, G);
-                for (int q = qs + l; q < qe; q += G)
-                    tile_insert<false>(keys, masks, logS, __ldg(&tilecol[q]), __ldg(&tilemask[q]), scal);
+                if (!live[d])
+                    break;
+                if (rc[d] >= 0)
+                    tile_insert<false>(keys, masks, logS, rc[d], rm[d], scal);
                 __syncwarp(gm);
+                live[d] = st.next(rc[d], rm[d], nv);
             }
         }
         int c = 0;
