@@ -111,6 +111,12 @@ struct mhb_context
     int num_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_vals = nullptr, ev_ready = nullptr;
+    static constexpr int kAux = 5; // per-bin kernels of one phase run concurrently (the reference uses 12 streams)
+    cudaStream_t aux[kAux] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
+    int aux_used = 0;
+    bool serial = false; // option "serial_bins": one stream, for per-kernel timing
+    DevBuf bsame;
     std::string err;
     // options
     int force_sym = 0, force_num = 0, verbose = 0;
@@ -163,6 +169,56 @@ int fail(mhb_context *h, int code, const std::string &msg)
         ++(h)->launches;                                                                                 \
         CU(cudaGetLastError());                                                                          \
     } while (0)
+
+#define LAUNCH_ON(h, st, kern, grid, block, smem, ...)                                                  \
+    do                                                                                                   \
+    {                                                                                                    \
+        kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                            \
+        ++(h)->launches;                                                                                 \
+        CU(cudaGetLastError());                                                                          \
+    } while (0)
+
+// Fork / join of the per-bin kernels of one phase: bin kernels are independent (disjoint rows,
+// disjoint outputs), so they are spread over the main stream and kAux helper streams.
+int fork_bins(mhb_context *h)
+{
+    h->aux_used = 0;
+    if (h->serial)
+        return MHB_OK;
+    CU(cudaEventRecord(h->ev_fork, h->stream));
+    return MHB_OK;
+}
+int next_bin_stream(mhb_context *h, cudaStream_t *out)
+{
+    if (h->serial)
+    {
+        *out = h->stream;
+        return MHB_OK;
+    }
+    int slot = h->aux_used++;
+    if (slot % (mhb_context::kAux + 1) == 0)
+    {
+        *out = h->stream;
+        return MHB_OK;
+    }
+    int a = slot % (mhb_context::kAux + 1) - 1;
+    if (slot <= mhb_context::kAux)
+        CU(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
+    *out = h->aux[a];
+    return MHB_OK;
+}
+int join_bins(mhb_context *h)
+{
+    if (h->serial)
+        return MHB_OK;
+    int n = std::min(h->aux_used - 1, (int)mhb_context::kAux);
+    for (int a = 0; a < n; ++a)
+    {
+        CU(cudaEventRecord(h->ev_join[a], h->aux[a]));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_join[a], 0));
+    }
+    return MHB_OK;
+}
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -233,6 +289,7 @@ int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
         {&h->tilecol, (size_t)(nnzB + 1) * 4},
         {&h->tilemask, (size_t)(nnzB + 1) * 4},
         {&h->binfo, (size_t)(K + 1) * 16},
+        {&h->bsame, (size_t)(K + 1)},
         {&h->arow, (size_t)(M + 1) * 16},
         {&h->binid, (size_t)(M + 1)},
         {&h->bins_sym, (size_t)(M + 1) * 4},
@@ -277,6 +334,9 @@ int build_mask_matrix(mhb_context *h, int K, int nnzB, const int *Bp, const int 
         LAUNCH(h, k_mask_fill, grid, 256, 0, Bc, nnz, nW, flags, wp, h->tilecol.as<int>(),
                h->tilemask.as<unsigned>());
     }
+    if (K > 0)
+        LAUNCH(h, k_mask_same, cdiv(K, 256), 256, 0, K, h->binfo.as<int4>(), h->tileptr.as<int>(),
+               h->tilecol.as<int>(), h->tilemask.as<unsigned>(), h->bsame.as<unsigned char>());
     return MHB_OK;
 }
 
@@ -302,48 +362,63 @@ int launch_symbolic_bins(mhb_context *h)
     int *counts = h->Cp;
     const int cap_blocks = h->num_sms * 16;
     int n;
+    cudaStream_t st;
+    int frc = fork_bins(h);
+    if (frc)
+        return frc;
     if ((n = n_of(SB_BM_G8)) > 0)
     {
         constexpr int G = 8, GPB = kSymThreads / G;
-        LAUNCH(h, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_G8_WORDS);
+               SB_BM_G8_WORDS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(SB_BM_WARP)) > 0)
     {
         constexpr int G = 32, GPB = kSymThreads / G;
-        LAUNCH(h, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_WARP_WORDS);
+               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(SB_BM_BLOCK)) > 0)
     {
         int words = std::min<long long>(SB_BM_BLOCK_WORDS, ((long long)h->N + 31) / 32 + 1);
-        LAUNCH(h, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
                n, h->Ap, h->Ac, tp, tc, tm, arow, counts);
     }
     if ((n = n_of(SB_H_G8)) > 0)
     {
         constexpr int G = 8, GPB = kSymThreads / G;
-        LAUNCH(h, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
                log2_ceil(SB_H_G8_SLOTS), scal);
     }
     if ((n = n_of(SB_H_WARP)) > 0)
     {
         constexpr int G = 32, GPB = kSymThreads / G;
-        LAUNCH(h, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
                log2_ceil(SB_H_WARP_SLOTS), scal);
     }
     if ((n = n_of(SB_H_BLOCK_S)) > 0)
-        LAUNCH(h, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
                bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal);
+    }
     if ((n = n_of(SB_H_BLOCK_L)) > 0)
-        LAUNCH(h, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
                bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal);
+    }
     if ((n = n_of(SB_H_GLOBAL)) > 0)
     {
         long long nt = ((long long)h->N + 31) / 32;
@@ -352,10 +427,11 @@ int launch_symbolic_bins(mhb_context *h)
         size_t slice = (size_t)slots * 2 * 4;
         int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 30) / slice));
         CU(h->pool.ensure(slice * nblk));
-        LAUNCH(h, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
                arow, counts, 0, h->pool.as<int>(), slots, scal);
     }
-    return MHB_OK;
+    return join_bins(h);
 }
 
 // ---- family 4 launches ------------------------------------------------------------------
@@ -370,11 +446,16 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     const int cap_blocks = h->num_sms * 16;
     const int *Ap = h->Ap, *Ac = h->Ac, *Bp = h->Bp, *Bc = h->Bc, *Cp = h->Cp;
     int n;
+    cudaStream_t st;
+    int frc = fork_bins(h);
+    if (frc)
+        return frc;
     if ((n = n_of(NB_WIN_G8)) > 0)
     {
         constexpr int G = 8, GPB = kNumGroupThreads / G;
         auto kern = k_num_win_group<G, T>;
-        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
                Cv, NB_WIN_G8_COLS);
     }
@@ -382,27 +463,31 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         constexpr int G = 32, GPB = kNumGroupThreads / G;
         auto kern = k_num_win_group<G, T>;
-        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, NB_WIN_WARP_COLS);
     }
     if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
     {
         int wcap = NB_WIN_BLOCK_S_COLS;
-        LAUNCH(h, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
                bins + off[NB_WIN_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
     if ((n = n_of(NB_WIN_BLOCK_L)) > 0)
     {
         int wcap = (int)std::min<long long>(NB_WIN_BLOCK_L_COLS, (((long long)h->N + 31) / 32) * 32);
-        LAUNCH(h, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
                bins + off[NB_WIN_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
     if ((n = n_of(NB_H_G8)) > 0)
     {
         constexpr int G = 8, GPB = kNumGroupThreads / G;
         auto kern = k_num_hash_group<G, T>;
-        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal);
     }
@@ -410,7 +495,8 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         constexpr int G = 32, GPB = kNumGroupThreads / G;
         auto kern = k_num_hash_group<G, T>;
-        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
     }
@@ -418,28 +504,36 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         constexpr int G = 32, GPB = kNumGroupThreads / G;
         auto kern = k_num_hash_group<G, T>;
-        LAUNCH(h, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS), scal);
     }
     if ((n = n_of(NB_H_BLOCK_S)) > 0)
-        LAUNCH(h, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
                bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
                (unsigned char *)nullptr, 0LL, scal);
+    }
     if ((n = n_of(NB_H_BLOCK_L)) > 0)
-        LAUNCH(h, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
                bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
                (unsigned char *)nullptr, 0LL, scal);
+    }
     if ((n = n_of(NB_H_GLOBAL)) > 0)
     {
         long long slots = 1LL << std::max(10, log2_ceil(2LL * h->max_rownnz));
         size_t slice = (size_t)slots * (sizeof(T) + 4);
         int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
         CU(h->pool.ensure(slice * nblk));
-        LAUNCH(h, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc,
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc,
                Cv, 0, h->pool.as<unsigned char>(), slots, scal);
     }
-    return MHB_OK;
+    return join_bins(h);
 }
 
 int set_kernel_attributes(mhb_context *h)
@@ -741,6 +835,12 @@ extern "C"
         for (auto &e : h->ev)
             if (cudaEventCreate(&e) != cudaSuccess)
                 return bail(MHB_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+            return bail(MHB_ERR_CUDA);
+        for (int a = 0; a < mhb_context::kAux; ++a)
+            if (cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming) != cudaSuccess)
+                return bail(MHB_ERR_CUDA);
         if (set_kernel_attributes(h) != MHB_OK)
         {
             std::fprintf(stderr, "mhb_create: %s\n", h->err.c_str());
@@ -757,7 +857,7 @@ extern "C"
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
-                          &h->binid, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
+                          &h->binid, &h->bsame, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
                           &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
                           &h->sC_col, &h->sC_val})
             b->release();
@@ -766,6 +866,15 @@ extern "C"
         for (auto &e : h->ev)
             if (e)
                 cudaEventDestroy(e);
+        for (int a = 0; a < mhb_context::kAux; ++a)
+        {
+            if (h->aux[a])
+                cudaStreamDestroy(h->aux[a]);
+            if (h->ev_join[a])
+                cudaEventDestroy(h->ev_join[a]);
+        }
+        if (h->ev_fork)
+            cudaEventDestroy(h->ev_fork);
         if (h->ev_vals)
             cudaEventDestroy(h->ev_vals);
         if (h->ev_ready)
@@ -797,6 +906,8 @@ extern "C"
             h->force_sym = (int)value;
         else if (k == "force_num_path")
             h->force_num = (int)value;
+        else if (k == "serial_bins")
+            h->serial = value != 0;
         else if (k == "verbose")
             h->verbose = (int)value;
         else

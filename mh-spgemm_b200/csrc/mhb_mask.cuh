@@ -133,4 +133,38 @@ __global__ void __launch_bounds__(256) k_mask_fill(const int *__restrict__ Bc, l
     }
 }
 
+// same[k] = 1 when row k of B has exactly the column pattern of row k-1 (equal tile lists).
+// Typical of multi-dof FEM matrices, where the rows of one node share their pattern.  The
+// symbolic pass skips such a row when it directly follows its twin in a row of A (OR is
+// idempotent); the numeric pass can fold the twins' products into one accumulator update.
+// One thread per row; the tile comparison stops at the first difference, so rows that are
+// not twins cost O(1).
+__global__ void __launch_bounds__(256) k_mask_same(int K, const int4 *__restrict__ binfo,
+                                                   const int *__restrict__ tileptr,
+                                                   const int *__restrict__ tilecol,
+                                                   const unsigned *__restrict__ tilemask,
+                                                   unsigned char *__restrict__ same)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K)
+        return;
+    unsigned char r = 0;
+    if (k > 0)
+    {
+        const int4 a = binfo[k - 1], b = binfo[k];
+        if (b.x > 0 && a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w)
+        {
+            const int pa = tileptr[k - 1], pb = tileptr[k];
+            r = 1;
+            for (int t = 0; t < b.y; ++t)
+                if (tilecol[pa + t] != tilecol[pb + t] || tilemask[pa + t] != tilemask[pb + t])
+                {
+                    r = 0;
+                    break;
+                }
+        }
+    }
+    same[k] = r;
+}
+
 } // namespace mhb

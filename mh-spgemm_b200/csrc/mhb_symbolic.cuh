@@ -28,12 +28,17 @@ constexpr int kSymThreads = 256;
 constexpr int kSymDepth = 4; // tile chunks in flight per group, see mhb_stream.cuh
 
 // ---- bitmap, G lanes per row -----------------------------------------------------------
+// Walks A's row G nonzeros at a time; the first tile chunk of B row i+1 is loaded before the
+// tiles of B row i are OR-ed in (L2 latency overlaps the shared-memory updates).  A B row
+// whose pattern equals the previous B row's (same[k]) and that directly follows it in A's
+// row contributes nothing new and is skipped.
 template <int G>
 __global__ void __launch_bounds__(kSymThreads)
     k_sym_bitmap_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                        const int *__restrict__ Ac, const int *__restrict__ tileptr,
                        const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
-                       const int4 *__restrict__ arow, int *__restrict__ counts, int wcap)
+                       const int4 *__restrict__ arow, int *__restrict__ counts, int wcap,
+                       const unsigned char *__restrict__ same)
 {
     extern __shared__ unsigned sm_u[];
     constexpr int GPB = kSymThreads / G;
@@ -50,27 +55,57 @@ __global__ void __launch_bounds__(kSymThreads)
             bm[w] = 0u;
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        ItemStream<G, NoVal, unsigned> st{Ac, nullptr, tileptr, tilecol, tilemask, gm, l};
-        st.init(s, e);
-        int rc[kSymDepth];
-        unsigned rm[kSymDepth];
-        bool live[kSymDepth];
-        NoVal nv;
-#pragma unroll
-        for (int d = 0; d < kSymDepth; ++d)
-            live[d] = st.next(rc[d], rm[d], nv);
-        while (live[0])
-        {
-#pragma unroll
-            for (int d = 0; d < kSymDepth; ++d)
+        int ts = 0, te = 0, kk = -2, nts = 0, nte = 0, nkk = -2;
+        auto load_meta = [&](int j, int &ms, int &me, int &mk) {
+            ms = 0, me = 0, mk = -2;
+            if (j < e)
             {
-                if (!live[d])
-                    break;
-                if (rc[d] >= 0)
-                    bm[rc[d] - tbase] |= rm[d]; // tiles of one B row are distinct: no atomic
-                __syncwarp(gm);
-                live[d] = st.next(rc[d], rm[d], nv);
+                mk = __ldg(&Ac[j]);
+                ms = __ldg(&tileptr[mk]);
+                me = __ldg(&tileptr[mk + 1]);
+                if (__ldg(&same[mk]))
+                    mk |= 0x40000000; // twin of row mk-1
             }
+        };
+        load_meta(s + l, ts, te, kk);
+        int prev_k = -2; // column of the last nonzero of the previous chunk
+        for (int j0 = s; j0 < e; j0 += G)
+        {
+            load_meta(j0 + G + l, nts, nte, nkk);
+            // drop rows that repeat the pattern of the nonzero just before them
+            int pk = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
+            if (l == 0)
+                pk = prev_k;
+            if ((kk & 0x40000000) && (kk & 0x3fffffff) == pk + 1)
+                te = ts;
+            prev_k = __shfl_sync(gm, kk & 0x3fffffff, G - 1, G);
+            const int cnt = min(G, e - j0);
+            int pc = -1, nq = 0, nqe = 0;
+            unsigned pm = 0u;
+            auto issue = [&](int i) {
+                nq = __shfl_sync(gm, ts, i, G);
+                nqe = __shfl_sync(gm, te, i, G);
+                pc = -1;
+                if (nq + l < nqe)
+                {
+                    pc = __ldg(&tilecol[nq + l]);
+                    pm = __ldg(&tilemask[nq + l]);
+                }
+            };
+            issue(0);
+            for (int i = 0; i < cnt; ++i)
+            {
+                const int c = pc, q = nq, qe = nqe;
+                const unsigned m = pm;
+                if (i + 1 < cnt)
+                    issue(i + 1);
+                if (c >= 0)
+                    bm[c - tbase] |= m; // tiles of one B row are distinct: no atomic
+                for (int p = q + G + l; p < qe; p += G)
+                    bm[__ldg(&tilecol[p]) - tbase] |= __ldg(&tilemask[p]);
+                __syncwarp(gm);
+            }
+            ts = nts, te = nte, kk = nkk;
         }
         int c = 0;
         for (int w = l; w < wt; w += G)
