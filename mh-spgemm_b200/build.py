@@ -40,5 +40,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_compat_driver() -> str:
+    """The reference-style C++ driver of tests/cpp (links the shim in mhb_compat.cu)."""
+    root = os.path.join(HERE, "..")
+    src = os.path.join(root, "tests", "cpp", "compat_driver.cu")
+    out = os.path.join(root, "tests", "cpp", "compat_driver")
+    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(root, "include"),
+                           "-o", out, src, "-L", HERE, "-lmhb_spgemm", "-Xlinker", "-rpath", "-Xlinker",
+                           "$ORIGIN/../../mh-spgemm_b200"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -69,9 +69,33 @@ def b_views(buf, K: int, nnzB: int, val_dtype):
     return ptr, col, val
 
 
+def exchange_B(Bbuf, world: int, src: int = 0):
+    """The one exchange step of the path: replicate B's packed image from its owner
+    (ncclBroadcast over NVLink / NVSwitch; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.broadcast(Bbuf, src=src)
+    return Bbuf
+
+
+def slice_offsets(nnz_local: int, rank: int, world: int, device):
+    """All-gather the per-rank nnz(C slice) (int64) -> (offset of this rank's slice in the
+    global col/val arrays, total nnz(C))."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor([nnz_local], dtype=torch.int64, device=device)
+    if world > 1:
+        allnnz = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allnnz, mine)
+    else:
+        allnnz = mine
+    sizes = allnnz.cpu().numpy()
+    return int(sizes[:rank].sum()), int(sizes.sum())
+
+
 class ShardedSpGEMM:
-    """C = A*B with A row-sharded over the ranks of `group`.  Each rank owns a Tool (one
-    handle per device) and the device arrays of its row block."""
+    """C = A*B with A row-sharded over the ranks.  Each rank owns a Tool (one handle per
+    device) and the device arrays of its row block."""
 
     def __init__(self, tool, rank: int, world: int, device=None):
         import torch
@@ -83,24 +107,15 @@ class ShardedSpGEMM:
         rank's rows; Bbuf = packed B image (valid on `src`, receive buffer elsewhere).
         Returns (C_ptr, C_col, C_val, slice_offset, total_nnz)."""
         import torch
-        import torch.distributed as dist
-        if self.world > 1:
-            dist.broadcast(Bbuf, src=src)  # the one exchange step of the path
+        exchange_B(Bbuf, self.world, src)
         bp, bc, bv = b_views(Bbuf, K, nnzB, val_dtype)
         Ml, ap, ac, av = A_blk
         cp, nnz = self.tool.symbolic(Ml, K, N, ap, ac, bp, bc)
         ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
         cval = torch.empty(max(nnz, 1), dtype=val_dtype, device=self.device)
         self.tool.numeric_into(av, bv, ccol, cval)
-        mine = torch.tensor([nnz], dtype=torch.int64, device=self.device)
-        if self.world > 1:
-            allnnz = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(allnnz, mine)
-        else:
-            allnnz = mine
-        sizes = allnnz.cpu().numpy()
-        off = int(sizes[:self.rank].sum())
-        return cp, ccol[:nnz], cval[:nnz], off, int(sizes.sum())
+        off, total = slice_offsets(nnz, self.rank, self.world, self.device)
+        return cp, ccol[:nnz], cval[:nnz], off, total
 
 
 def concat_slices(slices):
