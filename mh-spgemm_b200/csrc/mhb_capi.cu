@@ -488,7 +488,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv,
+               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal);
     }
     if ((n = n_of(NB_H_WARP_S)) > 0)
@@ -497,7 +497,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
+               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
     }
     if ((n = n_of(NB_H_WARP_L)) > 0)
@@ -506,21 +506,21 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp,
+               GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS), scal);
     }
     if ((n = n_of(NB_H_BLOCK_S)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
+               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
                (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_H_BLOCK_L)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
+               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
                (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_H_GLOBAL)) > 0)
@@ -530,7 +530,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
         CU(h->pool.ensure(slice * nblk));
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc,
+        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
                Cv, 0, h->pool.as<unsigned char>(), slots, scal);
     }
     return join_bins(h);

@@ -52,10 +52,10 @@ enum MhbNumBin
     NB_WIN_BLOCK_S, // dense window, block/row,   W <= 6144
     NB_WIN_BLOCK_L, // dense window, block/row,   W <= 27648 (216 KB of fp64 + flags)
     NB_H_G8,        // hash, 8 lanes/row, n <= 24  (32 slots)
-    NB_H_WARP_S,    // hash, warp/row,    n <= 192 (256 slots)
-    NB_H_WARP_L,    // hash, warp/row,    n <= 768 (1024 slots)
-    NB_H_BLOCK_S,   // hash, block/row,   n <= 3072 (4096 slots)
-    NB_H_BLOCK_L,   // hash, block/row,   n <= 12288 (16384 slots)
+    NB_H_WARP_S,    // hash, warp/row,    n <= 160 (256 slots; fill <= 5/8 leaves room for the sort scratch)
+    NB_H_WARP_L,    // hash, warp/row,    n <= 640 (1024 slots)
+    NB_H_BLOCK_S,   // hash, block/row,   n <= 2560 (4096 slots)
+    NB_H_BLOCK_L,   // hash, block/row,   n <= 10240 (16384 slots)
     NB_H_GLOBAL,    // hash in global memory
     NB_COUNT
 };
@@ -66,13 +66,13 @@ enum MhbNumBin
 #define NB_H_G8_SLOTS 32
 #define NB_H_G8_MAX 24
 #define NB_H_WARP_S_SLOTS 256
-#define NB_H_WARP_S_MAX 192
+#define NB_H_WARP_S_MAX 160
 #define NB_H_WARP_L_SLOTS 1024
-#define NB_H_WARP_L_MAX 768
+#define NB_H_WARP_L_MAX 640
 #define NB_H_BLOCK_S_SLOTS 4096
-#define NB_H_BLOCK_S_MAX 3072
+#define NB_H_BLOCK_S_MAX 2560
 #define NB_H_BLOCK_L_SLOTS 16384
-#define NB_H_BLOCK_L_MAX 12288
+#define NB_H_BLOCK_L_MAX 10240
 #define NB_WINDOW_WORK_FACTOR 32 // window when W <= 32 * n (or W <= 64)
 
 // path forcing (mhb_set_option "force_sym_path"/"force_num_path")

@@ -28,7 +28,6 @@ namespace mhb
 {
 
 constexpr int kNumGroupThreads = 256;
-constexpr int kNumDepth = 4; // items (chunks of B) in flight per group, see mhb_stream.cuh
 constexpr int kPre = 3;      // chunks of the next B row prefetched by the dense-window kernel
 
 // =========================================================================================
@@ -56,77 +55,12 @@ __global__ void __launch_bounds__(kNumGroupThreads)
             acc[i] = Unset<T>::value();
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        // Walk A's row 32 (G) nonzeros at a time.  The first kPre chunks of the B row of
-        // nonzero i+1 are loaded into registers before nonzero i is accumulated, so the L2
-        // latency of B overlaps the shared-memory updates; the A-side metadata of the next
-        // G nonzeros is prefetched the same way.
-        int bs = 0, be = 0, nbs = 0, nbe = 0;
-        T av = T(0), nav = T(0);
-        auto load_meta = [&](int j, int &ms, int &me, T &ma) {
-            ms = 0, me = 0, ma = T(0);
-            if (j < e)
-            {
-                const int k = __ldg(&Ac[j]);
-                ma = __ldg(&Av[j]);
-                ms = __ldg(&Bp[k]);
-                me = __ldg(&Bp[k + 1]);
-            }
-        };
-        load_meta(s + l, bs, be, av);
-        for (int j0 = s; j0 < e; j0 += G)
-        {
-            load_meta(j0 + G + l, nbs, nbe, nav);
-            const int cnt = min(G, e - j0);
-            int pc[kPre], nq = 0, nqe = 0;
-            T pv[kPre], na = T(0);
-            auto issue = [&](int i) {
-                nq = __shfl_sync(gm, bs, i, G);
-                nqe = __shfl_sync(gm, be, i, G);
-                na = __shfl_sync(gm, av, i, G);
-#pragma unroll
-                for (int t = 0; t < kPre; ++t)
-                {
-                    const int p = nq + t * G + l;
-                    pc[t] = -1;
-                    if (p < nqe)
-                    {
-                        pc[t] = __ldg(&Bc[p]);
-                        pv[t] = __ldg(&Bv[p]);
-                    }
-                }
-            };
-            issue(0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                int cc[kPre];
-                T cv[kPre];
-                const int q = nq, qe = nqe;
-                const T a = na;
-#pragma unroll
-                for (int t = 0; t < kPre; ++t)
-                    cc[t] = pc[t], cv[t] = pv[t];
-                if (i + 1 < cnt)
-                    issue(i + 1);
-                // the columns of one B row are distinct: plain read-modify-write, no atomics
-#pragma unroll
-                for (int t = 0; t < kPre; ++t)
-                    if (cc[t] >= 0)
-                    {
-                        const int idx = cc[t] - cmin;
-                        const T o = acc[idx];
-                        acc[idx] = Unset<T>::is(o) ? a * cv[t] : fma(a, cv[t], o);
-                    }
-                for (int p = q + kPre * G + l; p < qe; p += G) // rows longer than kPre*G
-                {
-                    const int idx = __ldg(&Bc[p]) - cmin;
-                    const T v = __ldg(&Bv[p]);
-                    const T o = acc[idx];
-                    acc[idx] = Unset<T>::is(o) ? a * v : fma(a, v, o);
-                }
-                __syncwarp(gm); // order this B row's stores before the next row's loads
-            }
-            bs = nbs, be = nbe, av = nav;
-        }
+        // the columns of one B row are distinct: plain read-modify-write, no atomics
+        walk_sequential<G, kPre, T, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+            const int idx = c - cmin;
+            const T o = acc[idx];
+            acc[idx] = Unset<T>::is(o) ? a * v : fma(a, v, o);
+        });
         // ordered compaction: the window is already sorted by column
         int out = __ldg(&Cp[row]);
         for (int i0 = 0; i0 < W; i0 += G)
@@ -209,32 +143,13 @@ __global__ void k_num_win_block(const int *__restrict__ rows, int nrows, const i
             flags[i] = 0u;
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
-        {
-            int bs = 0, be = 0;
-            T av = T(0);
-            if (j0 + lane < e)
-            {
-                const int k = __ldg(&Ac[j0 + lane]);
-                av = __ldg(&Av[j0 + lane]);
-                bs = __ldg(&Bp[k]);
-                be = __ldg(&Bp[k + 1]);
-            }
-            const int cnt = min(32, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(kFull, bs, i), qe = __shfl_sync(kFull, be, i);
-                const T a = __shfl_sync(kFull, av, i);
-                for (int q = qs + lane; q < qe; q += 32)
-                {
-                    const int idx = __ldg(&Bc[q]) - cmin;
-                    atomicAdd(&acc[idx], a * __ldg(&Bv[q]));
-                    const unsigned bit = 1u << (idx & 31);
-                    if (!(flags[idx >> 5] & bit))
-                        atomicOr(&flags[idx >> 5], bit);
-                }
-            }
-        }
+        walk_flat<32, T, T>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+            const int idx = c - cmin;
+            atomicAdd(&acc[idx], a * v);
+            const unsigned bit = 1u << (idx & 31);
+            if (!(flags[idx >> 5] & bit))
+                atomicOr(&flags[idx >> 5], bit);
+        });
         __syncthreads();
         // prefix of the per-word popcounts -> output position of every present column
         int carry = 0;
@@ -318,13 +233,161 @@ __device__ __forceinline__ void bitonic_sort_kv(int *keys, T *vals, int P, int t
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Bucket-rank sort of the compacted (keys[0..n), vals[0..n)) of one C row, emitted straight
+// into C.  The first profile of the hash kernels (profiles/r1b_*) showed the bitonic sort
+// taking ~2/3 of their instructions.  Columns of a C row lie in [cmin, cmin + W): bucket =
+// (key - cmin) >> sh splits that span into NB = S/8 equal ranges (a counting sort on the
+// top bits), and inside a bucket (a handful of keys) the rank is found by direct
+// comparison.  Scratch lives in the unused tail of the table (fill <= 5/8):
+//   keys[n ..]            : start[NB+1], cursor[NB]      (NB = S/8  ->  S/4+1 ints <= 3S/8)
+//   vals[n ..] as ushort  : idx[n] = indices grouped by bucket (2n bytes <= (S-n)*sizeof(T))
+// ~40 instructions per element instead of ~220 (n = 640).  Returns false without emitting
+// when one bucket holds more than kBucketMax keys (heavily clustered columns): the caller
+// then falls back to the bitonic sort.
+// -----------------------------------------------------------------------------------------
+constexpr int kBucketMax = 96;
+
+__device__ __forceinline__ int ceil_log2_dev(int v) { return v <= 1 ? 0 : 32 - __clz(v - 1); }
+
+template <typename T>
+__device__ __forceinline__ bool bucket_sort_emit_warp(int *keys, T *vals, int n, int logS, int cmin, int W,
+                                                      int l, int *__restrict__ Cc, T *__restrict__ Cv)
+{
+    const int logNB = logS - 3, NB = 1 << logNB;
+    const int sh = max(0, ceil_log2_dev(W) - logNB);
+    int *start = keys + n;            // NB + 1
+    int *cursor = start + NB + 1;     // NB
+    unsigned short *idx = reinterpret_cast<unsigned short *>(vals + n);
+    for (int b = l; b < NB; b += 32)
+    {
+        start[b] = 0;
+        cursor[b] = 0;
+    }
+    __syncwarp();
+    for (int i = l; i < n; i += 32)
+        atomicAdd(&start[(keys[i] - cmin) >> sh], 1);
+    __syncwarp();
+    // exclusive scan of the NB counts: lane l owns NB/32 consecutive buckets (NB >= 32)
+    const int per = NB >> 5; // 1 (S = 256) or 4 (S = 1024)
+    int cnt[4], tot = 0, mx = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+    {
+        cnt[t] = (t < per) ? start[l * per + t] : 0;
+        tot += cnt[t];
+        mx = max(mx, cnt[t]);
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (l >= o)
+            incl += t;
+    }
+    mx = group_max<32>(mx, kFull);
+    if (mx > kBucketMax)
+        return false;
+    int run = incl - tot;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (t < per)
+        {
+            start[l * per + t] = run;
+            run += cnt[t];
+        }
+    if (l == 31)
+        start[NB] = n;
+    __syncwarp();
+    for (int i = l; i < n; i += 32)
+    {
+        const int b = (keys[i] - cmin) >> sh;
+        idx[start[b] + atomicAdd(&cursor[b], 1)] = (unsigned short)i;
+    }
+    __syncwarp();
+    for (int p = l; p < n; p += 32)
+    {
+        const int i = idx[p];
+        const int k = keys[i];
+        const int b = (k - cmin) >> sh;
+        const int lo = start[b], hi = start[b + 1];
+        int rank = lo;
+        for (int q = lo; q < hi; ++q)
+            rank += keys[idx[q]] < k;
+        Cc[rank] = k;
+        Cv[rank] = vals[i];
+    }
+    return true;
+}
+
+// Block-wide variant (one block per row, S up to 16 384): same layout, scan via block_excl_scan.
+template <typename T>
+__device__ __forceinline__ bool bucket_sort_emit_block(int *keys, T *vals, int n, int logS, int cmin, int W,
+                                                       int *warp_tot, int *__restrict__ Cc,
+                                                       T *__restrict__ Cv)
+{
+    const int logNB = logS - 3, NB = 1 << logNB;
+    const int sh = max(0, ceil_log2_dev(W) - logNB);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int *start = keys + n;
+    int *cursor = start + NB + 1;
+    unsigned short *idx = reinterpret_cast<unsigned short *>(vals + n);
+    for (int b = tid; b < NB; b += nthr)
+    {
+        start[b] = 0;
+        cursor[b] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr)
+        atomicAdd(&start[(keys[i] - cmin) >> sh], 1);
+    __syncthreads();
+    int carry = 0, mx = 0;
+    for (int b0 = 0; b0 < NB; b0 += nthr)
+    {
+        const int b = b0 + tid;
+        const int c = (b < NB) ? start[b] : 0;
+        mx = max(mx, c);
+        int tot;
+        const int ex = block_excl_scan(c, warp_tot, &tot);
+        if (b < NB)
+            start[b] = carry + ex;
+        carry += tot;
+    }
+    if (tid == 0)
+        start[NB] = n;
+    const bool bad = __syncthreads_or(mx > kBucketMax);
+    if (bad)
+        return false;
+    for (int i = tid; i < n; i += nthr)
+    {
+        const int b = (keys[i] - cmin) >> sh;
+        idx[start[b] + atomicAdd(&cursor[b], 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += nthr)
+    {
+        const int i = idx[p];
+        const int k = keys[i];
+        const int b = (k - cmin) >> sh;
+        const int lo = start[b], hi = start[b + 1];
+        int rank = lo;
+        for (int q = lo; q < hi; ++q)
+            rank += keys[idx[q]] < k;
+        Cc[rank] = k;
+        Cv[rank] = vals[i];
+    }
+    return true;
+}
+
 // ---- hash, G lanes per row, table of 2^logS (key, value) slots per group -----------------
 template <int G, typename T>
 __global__ void __launch_bounds__(kNumGroupThreads)
     k_num_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
-                     const int *__restrict__ Bc, const T *__restrict__ Bv, const int *__restrict__ Cp,
-                     int *__restrict__ Cc, T *__restrict__ Cv, int logS, int *__restrict__ scal)
+                     const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
+                     const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
+                     int *__restrict__ scal)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int GPB = kNumGroupThreads / G;
@@ -344,33 +407,26 @@ __global__ void __launch_bounds__(kNumGroupThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        ItemStream<G, T, T> st{Ac, Av, Bp, Bc, Bv, gm, l};
-        st.init(s, e);
-        int rc[kNumDepth];
-        T rv[kNumDepth], ra[kNumDepth];
-        bool live[kNumDepth];
-#pragma unroll
-        for (int d = 0; d < kNumDepth; ++d)
-            live[d] = st.next(rc[d], rv[d], ra[d]);
-        while (live[0])
-        {
-#pragma unroll
-            for (int d = 0; d < kNumDepth; ++d)
-            {
-                if (!live[d])
-                    break;
-                if (rc[d] >= 0)
-                {
-                    const int h = key_slot(keys, logS, rc[d]);
-                    if (h >= 0)
-                        vals[h] = fma(ra[d], rv[d], vals[h]); // columns of one item are distinct: no atomic
-                    else
-                        atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
-                }
-                __syncwarp(gm);
-                live[d] = st.next(rc[d], rv[d], ra[d]);
-            }
-        }
+        // B rows long enough to fill the group: sequential walk, plain accumulate.  Short B
+        // rows (power-law graphs): flat expansion, all lanes busy, atomic accumulate.
+        const int products = __ldg(&arow[row]).x;
+        if ((long long)products * 2 >= (long long)(e - s) * G)
+            walk_sequential<G, 2, T, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+                const int h = key_slot(keys, logS, c);
+                if (h >= 0)
+                    vals[h] = fma(a, v, vals[h]);
+                else
+                    atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+            });
+        else
+            walk_flat<G, T, T>(gm, l, s, e, G, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+                const int h = key_slot(keys, logS, c);
+                if (h >= 0)
+                    atomicAdd(&vals[h], a * v);
+                else
+                    atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+            });
+        __syncwarp(gm);
         // in-place compaction to the front of the table, G slots per step
         int n = 0;
         for (int i0 = 0; i0 < S; i0 += G)
@@ -403,19 +459,36 @@ __global__ void __launch_bounds__(kNumGroupThreads)
                 Cv[out + rank] = vals[i];
             }
         }
+        else if (n <= 32)
+        {
+            // one key per lane: rank by direct comparison
+            const int k = (l < n) ? keys[l] : INT_MAX;
+            int rank = 0;
+            for (int j = 0; j < n; ++j)
+                rank += keys[j] < k;
+            if (l < n)
+            {
+                Cc[out + rank] = k;
+                Cv[out + rank] = vals[l];
+            }
+        }
         else
         {
-            int P = 2;
-            while (P < n)
-                P <<= 1;
-            for (int i = n + l; i < P; i += G)
-                keys[i] = INT_MAX;
-            __syncwarp(gm);
-            bitonic_sort_kv(keys, vals, P, l, G, [&]() { __syncwarp(gm); });
-            for (int i = l; i < n; i += G)
+            const int4 info = __ldg(&arow[row]);
+            if (!bucket_sort_emit_warp<T>(keys, vals, n, logS, info.z, info.w - info.z + 1, l, Cc + out, Cv + out))
             {
-                Cc[out + i] = keys[i];
-                Cv[out + i] = vals[i];
+                int P = 2;
+                while (P < n)
+                    P <<= 1;
+                for (int i = n + l; i < P; i += G)
+                    keys[i] = INT_MAX;
+                __syncwarp(gm);
+                bitonic_sort_kv(keys, vals, P, l, G, [&]() { __syncwarp(gm); });
+                for (int i = l; i < n; i += G)
+                {
+                    Cc[out + i] = keys[i];
+                    Cv[out + i] = vals[i];
+                }
             }
         }
         __syncwarp(gm);
@@ -427,8 +500,9 @@ template <typename T>
 __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                                  const int *__restrict__ Ac, const T *__restrict__ Av,
                                  const int *__restrict__ Bp, const int *__restrict__ Bc,
-                                 const T *__restrict__ Bv, const int *__restrict__ Cp, int *__restrict__ Cc,
-                                 T *__restrict__ Cv, int logS_fixed, unsigned char *__restrict__ pool,
+                                 const T *__restrict__ Bv, const int4 *__restrict__ arow,
+                                 const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv,
+                                 int logS_fixed, unsigned char *__restrict__ pool,
                                  long long pool_slots, int *__restrict__ scal)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -464,34 +538,13 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
         }
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
-        {
-            int bs = 0, be = 0;
-            T av = T(0);
-            if (j0 + lane < e)
-            {
-                const int k = __ldg(&Ac[j0 + lane]);
-                av = __ldg(&Av[j0 + lane]);
-                bs = __ldg(&Bp[k]);
-                be = __ldg(&Bp[k + 1]);
-            }
-            const int cnt = min(32, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(kFull, bs, i), qe = __shfl_sync(kFull, be, i);
-                const T a = __shfl_sync(kFull, av, i);
-                for (int q = qs + lane; q < qe; q += 32)
-                {
-                    const int c = __ldg(&Bc[q]);
-                    const T v = __ldg(&Bv[q]);
-                    const int h = key_slot(keys, logS, c);
-                    if (h >= 0)
-                        atomicAdd(&vals[h], a * v);
-                    else
-                        atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
-                }
-            }
-        }
+        walk_flat<32, T, T>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+            const int h = key_slot(keys, logS, c);
+            if (h >= 0)
+                atomicAdd(&vals[h], a * v);
+            else
+                atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+        });
         __syncthreads();
         // in-place compaction, blockDim slots per step
         int n = 0;
@@ -516,17 +569,27 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
             n += tot;
             __syncthreads();
         }
-        int P = 2;
-        while (P < n)
-            P <<= 1;
-        for (int i = n + threadIdx.x; i < P; i += blockDim.x)
-            keys[i] = INT_MAX;
-        __syncthreads();
-        bitonic_sort_kv(keys, vals, P, (int)threadIdx.x, (int)blockDim.x, [&]() { __syncthreads(); });
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        bool done = false;
+        if (!pool && n > 0)
         {
-            Cc[out + i] = keys[i];
-            Cv[out + i] = vals[i];
+            const int4 info = __ldg(&arow[row]);
+            done = bucket_sort_emit_block<T>(keys, vals, n, logS, info.z, info.w - info.z + 1, warp_tot, Cc + out,
+                                             Cv + out);
+        }
+        if (!done)
+        {
+            int P = 2;
+            while (P < n)
+                P <<= 1;
+            for (int i = n + threadIdx.x; i < P; i += blockDim.x)
+                keys[i] = INT_MAX;
+            __syncthreads();
+            bitonic_sort_kv(keys, vals, P, (int)threadIdx.x, (int)blockDim.x, [&]() { __syncthreads(); });
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                Cc[out + i] = keys[i];
+                Cv[out + i] = vals[i];
+            }
         }
         __syncthreads();
     }

@@ -25,7 +25,6 @@ namespace mhb
 {
 
 constexpr int kSymThreads = 256;
-constexpr int kSymDepth = 4; // tile chunks in flight per group, see mhb_stream.cuh
 
 // ---- bitmap, G lanes per row -----------------------------------------------------------
 // Walks A's row G nonzeros at a time; the first tile chunk of B row i+1 is loaded before the
@@ -154,24 +153,13 @@ __global__ void __launch_bounds__(kSymThreads)
             bm[w] = 0u;
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        // each warp takes 32 entries of A's row at a time; lanes fetch the tile ranges
-        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
-        {
-            int ts = 0, te = 0;
-            if (j0 + lane < e)
-            {
-                int k = __ldg(&Ac[j0 + lane]);
-                ts = __ldg(&tileptr[k]);
-                te = __ldg(&tileptr[k + 1]);
-            }
-            const int cnt = min(32, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(kFull, ts, i), qe = __shfl_sync(kFull, te, i);
-                for (int q = qs + lane; q < qe; q += 32)
-                    atomicOr(&bm[__ldg(&tilecol[q]) - tbase], __ldg(&tilemask[q]));
-            }
-        }
+        // every warp takes 32 nonzeros of A at a time and expands their tile lists flat
+        walk_flat<32, NoVal, unsigned>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, (const NoVal *)nullptr,
+                                       tileptr, tilecol, tilemask, [&](int tc, unsigned m, NoVal) {
+                                           unsigned *w = &bm[tc - tbase];
+                                           if ((*w & m) != m)
+                                               atomicOr(w, m);
+                                       });
         __syncthreads();
         int c = 0;
         for (int w = threadIdx.x; w < wt; w += blockDim.x)
@@ -239,28 +227,11 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        ItemStream<G, NoVal, unsigned> st{Ac, nullptr, tileptr, tilecol, tilemask, gm, l};
-        st.init(s, e);
-        int rc[kSymDepth];
-        unsigned rm[kSymDepth];
-        bool live[kSymDepth];
-        NoVal nv;
-#pragma unroll
-        for (int d = 0; d < kSymDepth; ++d)
-            live[d] = st.next(rc[d], rm[d], nv);
-        while (live[0])
-        {
-#pragma unroll
-            for (int d = 0; d < kSymDepth; ++d)
-            {
-                if (!live[d])
-                    break;
-                if (rc[d] >= 0)
-                    tile_insert<false>(keys, masks, logS, rc[d], rm[d], scal);
-                __syncwarp(gm);
-                live[d] = st.next(rc[d], rm[d], nv);
-            }
-        }
+        walk_flat<G, NoVal, unsigned>(gm, l, s, e, G, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
+                                      [&](int tc, unsigned m, NoVal) {
+                                          tile_insert<true>(keys, masks, logS, tc, m, scal);
+                                      });
+        __syncwarp(gm);
         int c = 0;
         for (int w = l; w < S; w += G)
             c += __popc(masks[w]);
@@ -310,23 +281,10 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j0 = s + warp * 32; j0 < e; j0 += nwarp * 32)
-        {
-            int ts = 0, te = 0;
-            if (j0 + lane < e)
-            {
-                int k = __ldg(&Ac[j0 + lane]);
-                ts = __ldg(&tileptr[k]);
-                te = __ldg(&tileptr[k + 1]);
-            }
-            const int cnt = min(32, e - j0);
-            for (int i = 0; i < cnt; ++i)
-            {
-                const int qs = __shfl_sync(kFull, ts, i), qe = __shfl_sync(kFull, te, i);
-                for (int q = qs + lane; q < qe; q += 32)
-                    tile_insert<true>(keys, masks, logS, __ldg(&tilecol[q]), __ldg(&tilemask[q]), scal);
-            }
-        }
+        walk_flat<32, NoVal, unsigned>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, (const NoVal *)nullptr,
+                                       tileptr, tilecol, tilemask, [&](int tc, unsigned m, NoVal) {
+                                           tile_insert<true>(keys, masks, logS, tc, m, scal);
+                                       });
         __syncthreads();
         int c = 0;
         for (int w = threadIdx.x; w < S; w += blockDim.x)
