@@ -143,7 +143,7 @@ __global__ void k_num_win_block(const int *__restrict__ rows, int nrows, const i
             flags[i] = 0u;
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<32, T, T>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+        walk_flat<32, T, T>(kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
             const int idx = c - cmin;
             atomicAdd(&acc[idx], a * v);
             const unsigned bit = 1u << (idx & 31);
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kNumGroupThreads)
                     atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
             });
         else
-            walk_flat<G, T, T>(gm, l, s, e, G, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+            walk_flat<G, T, T>(gm, l, s, e, 0, 1, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
                 const int h = key_slot(keys, logS, c);
                 if (h >= 0)
                     atomicAdd(&vals[h], a * v);
@@ -538,7 +538,7 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
         }
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<32, T, T>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+        walk_flat<32, T, T>(kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
             const int h = key_slot(keys, logS, c);
             if (h >= 0)
                 atomicAdd(&vals[h], a * v);

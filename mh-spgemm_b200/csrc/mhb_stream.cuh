@@ -116,10 +116,13 @@ __device__ __forceinline__ void walk_sequential(unsigned gm, int l, int s, int e
 }
 
 // update(c, v, a) must be atomic with respect to the other lanes of the group.
-// The group takes G nonzeros of A at j0 = s, s + jstride, ... (jstride = G for a group that
-// owns the row; = 32 * warps for the warps of a block that share one row).
+// Every group walks ALL chunks of G nonzeros of A (j0 = s, s + G, ...); the products of a
+// chunk are split between the `tparts` groups sharing the row: this group takes products
+// tpart*G + l, (tpart + tparts)*G + l, ...  (tparts = 1 for a group that owns its row; the
+// warps of a block that share one row pass their warp index / warp count, so that rows of A
+// with few nonzeros still keep every warp of the block busy).
 template <int G, typename TA, typename TB, class Update>
-__device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int jstride,
+__device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int tpart, int tparts,
                                           const int *__restrict__ Ac, const TA *__restrict__ Av,
                                           const int *__restrict__ Bp, const int *__restrict__ Bc,
                                           const TB *__restrict__ Bv, Update update)
@@ -127,9 +130,9 @@ __device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int 
     int bs, be, nbs, nbe;
     TA av, nav;
     load_meta<TA>(s + l, e, Ac, Av, Bp, bs, be, av);
-    for (int j0 = s; j0 < e; j0 += jstride)
+    for (int j0 = s; j0 < e; j0 += G)
     {
-        load_meta<TA>(j0 + jstride + l, e, Ac, Av, Bp, nbs, nbe, nav);
+        load_meta<TA>(j0 + G + l, e, Ac, Av, Bp, nbs, nbe, nav);
         const int len = be - bs;
         int incl = len;
 #pragma unroll
@@ -142,7 +145,7 @@ __device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int 
         const int off = incl - len;
         const int total = __shfl_sync(gm, incl, G - 1, G);
         const int base = bs - off;
-        for (int t0 = 0; t0 < total; t0 += G)
+        for (int t0 = tpart * G; t0 < total; t0 += tparts * G)
         {
             const int t = t0 + l;
             int ent = 0;

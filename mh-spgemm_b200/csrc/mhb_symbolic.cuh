@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kSymThreads)
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         // every warp takes 32 nonzeros of A at a time and expands their tile lists flat
-        walk_flat<32, NoVal, unsigned>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, (const NoVal *)nullptr,
+        walk_flat<32, NoVal, unsigned>(kFull, lane, s, e, warp, nwarp, Ac, (const NoVal *)nullptr,
                                        tileptr, tilecol, tilemask, [&](int tc, unsigned m, NoVal) {
                                            unsigned *w = &bm[tc - tbase];
                                            if ((*w & m) != m)
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<G, NoVal, unsigned>(gm, l, s, e, G, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
+        walk_flat<G, NoVal, unsigned>(gm, l, s, e, 0, 1, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
                                       [&](int tc, unsigned m, NoVal) {
                                           tile_insert<true>(keys, masks, logS, tc, m, scal);
                                       });
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<32, NoVal, unsigned>(kFull, lane, s + warp * 32, e, nwarp * 32, Ac, (const NoVal *)nullptr,
+        walk_flat<32, NoVal, unsigned>(kFull, lane, s, e, warp, nwarp, Ac, (const NoVal *)nullptr,
                                        tileptr, tilecol, tilemask, [&](int tc, unsigned m, NoVal) {
                                            tile_insert<true>(keys, masks, logS, tc, m, scal);
                                        });
