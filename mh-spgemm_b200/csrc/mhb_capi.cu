@@ -195,14 +195,16 @@ int next_bin_stream(mhb_context *h, cudaStream_t *out)
         *out = h->stream;
         return MHB_OK;
     }
+    // slots 0..kAux-1 -> helper streams (the first, big-row bins land on the high-priority
+    // ones), slot kAux -> main stream, then round robin
     int slot = h->aux_used++;
-    if (slot % (mhb_context::kAux + 1) == 0)
+    int a = slot % (mhb_context::kAux + 1);
+    if (a == mhb_context::kAux)
     {
         *out = h->stream;
         return MHB_OK;
     }
-    int a = slot % (mhb_context::kAux + 1) - 1;
-    if (slot <= mhb_context::kAux)
+    if (slot < mhb_context::kAux)
         CU(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
     *out = h->aux[a];
     return MHB_OK;
@@ -211,7 +213,7 @@ int join_bins(mhb_context *h)
 {
     if (h->serial)
         return MHB_OK;
-    int n = std::min(h->aux_used - 1, (int)mhb_context::kAux);
+    int n = std::min(h->aux_used, (int)mhb_context::kAux);
     for (int a = 0; a < n; ++a)
     {
         CU(cudaEventRecord(h->ev_join[a], h->aux[a]));
@@ -366,59 +368,7 @@ int launch_symbolic_bins(mhb_context *h)
     int frc = fork_bins(h);
     if (frc)
         return frc;
-    if ((n = n_of(SB_BM_G8)) > 0)
-    {
-        constexpr int G = 8, GPB = kSymThreads / G;
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_G8_WORDS, h->bsame.as<unsigned char>());
-    }
-    if ((n = n_of(SB_BM_WARP)) > 0)
-    {
-        constexpr int G = 32, GPB = kSymThreads / G;
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>());
-    }
-    if ((n = n_of(SB_BM_BLOCK)) > 0)
-    {
-        int words = std::min<long long>(SB_BM_BLOCK_WORDS, ((long long)h->N + 31) / 32 + 1);
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
-               n, h->Ap, h->Ac, tp, tc, tm, arow, counts);
-    }
-    if ((n = n_of(SB_H_G8)) > 0)
-    {
-        constexpr int G = 8, GPB = kSymThreads / G;
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
-               log2_ceil(SB_H_G8_SLOTS), scal);
-    }
-    if ((n = n_of(SB_H_WARP)) > 0)
-    {
-        constexpr int G = 32, GPB = kSymThreads / G;
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
-               log2_ceil(SB_H_WARP_SLOTS), scal);
-    }
-    if ((n = n_of(SB_H_BLOCK_S)) > 0)
-    {
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
-               bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal);
-    }
-    if ((n = n_of(SB_H_BLOCK_L)) > 0)
-    {
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
-               bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal);
-    }
+    // big-row bins first (see launch_numeric_bins)
     if ((n = n_of(SB_H_GLOBAL)) > 0)
     {
         long long nt = ((long long)h->N + 31) / 32;
@@ -430,6 +380,59 @@ int launch_symbolic_bins(mhb_context *h)
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
                arow, counts, 0, h->pool.as<int>(), slots, scal);
+    }
+    if ((n = n_of(SB_H_BLOCK_L)) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
+               bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal);
+    }
+    if ((n = n_of(SB_BM_BLOCK)) > 0)
+    {
+        int words = std::min<long long>(SB_BM_BLOCK_WORDS, ((long long)h->N + 31) / 32 + 1);
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
+               n, h->Ap, h->Ac, tp, tc, tm, arow, counts);
+    }
+    if ((n = n_of(SB_H_BLOCK_S)) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
+               bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal);
+    }
+    if ((n = n_of(SB_H_WARP)) > 0)
+    {
+        constexpr int G = 32, GPB = kSymThreads / G;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               log2_ceil(SB_H_WARP_SLOTS), scal);
+    }
+    if ((n = n_of(SB_BM_WARP)) > 0)
+    {
+        constexpr int G = 32, GPB = kSymThreads / G;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>());
+    }
+    if ((n = n_of(SB_H_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kSymThreads / G;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               log2_ceil(SB_H_G8_SLOTS), scal);
+    }
+    if ((n = n_of(SB_BM_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kSymThreads / G;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               SB_BM_G8_WORDS, h->bsame.as<unsigned char>());
     }
     return join_bins(h);
 }
@@ -450,30 +453,24 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     int frc = fork_bins(h);
     if (frc)
         return frc;
-    if ((n = n_of(NB_WIN_G8)) > 0)
+    // launch order: bins with the fewest, largest rows first, so that their long-running
+    // blocks start at once and overlap the bulk bins instead of forming a tail
+    if ((n = n_of(NB_H_GLOBAL)) > 0)
     {
-        constexpr int G = 8, GPB = kNumGroupThreads / G;
-        auto kern = k_num_win_group<G, T>;
+        long long slots = 1LL << std::max(10, log2_ceil(2LL * h->max_rownnz));
+        size_t slice = (size_t)slots * (sizeof(T) + 4);
+        int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
+        CU(h->pool.ensure(slice * nblk));
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
-               Cv, NB_WIN_G8_COLS);
+        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
+               Cv, 0, h->pool.as<unsigned char>(), slots, scal);
     }
-    if ((n = n_of(NB_WIN_WARP)) > 0)
+    if ((n = n_of(NB_H_BLOCK_L)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, NB_WIN_WARP_COLS);
-    }
-    if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
-    {
-        int wcap = NB_WIN_BLOCK_S_COLS;
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
-               bins + off[NB_WIN_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
+               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
+               (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_WIN_BLOCK_L)) > 0)
     {
@@ -482,23 +479,19 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
                bins + off[NB_WIN_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
-    if ((n = n_of(NB_H_G8)) > 0)
+    if ((n = n_of(NB_H_BLOCK_S)) > 0)
     {
-        constexpr int G = 8, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-               log2_ceil(NB_H_G8_SLOTS), scal);
+        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
+               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
+               (unsigned char *)nullptr, 0LL, scal);
     }
-    if ((n = n_of(NB_H_WARP_S)) > 0)
+    if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
+        int wcap = NB_WIN_BLOCK_S_COLS;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+        LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
+               bins + off[NB_WIN_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
     if ((n = n_of(NB_H_WARP_L)) > 0)
     {
@@ -509,29 +502,41 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
                GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS), scal);
     }
-    if ((n = n_of(NB_H_BLOCK_S)) > 0)
+    if ((n = n_of(NB_WIN_WARP)) > 0)
     {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
-               (unsigned char *)nullptr, 0LL, scal);
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               Cc, Cv, NB_WIN_WARP_COLS);
     }
-    if ((n = n_of(NB_H_BLOCK_L)) > 0)
+    if ((n = n_of(NB_H_WARP_S)) > 0)
     {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
-               (unsigned char *)nullptr, 0LL, scal);
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
     }
-    if ((n = n_of(NB_H_GLOBAL)) > 0)
+    if ((n = n_of(NB_WIN_G8)) > 0)
     {
-        long long slots = 1LL << std::max(10, log2_ceil(2LL * h->max_rownnz));
-        size_t slice = (size_t)slots * (sizeof(T) + 4);
-        int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
-        CU(h->pool.ensure(slice * nblk));
+        constexpr int G = 8, GPB = kNumGroupThreads / G;
+        auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
-               Cv, 0, h->pool.as<unsigned char>(), slots, scal);
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
+               Cv, NB_WIN_G8_COLS);
+    }
+    if ((n = n_of(NB_H_G8)) > 0)
+    {
+        constexpr int G = 8, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+               log2_ceil(NB_H_G8_SLOTS), scal);
     }
     return join_bins(h);
 }
@@ -837,8 +842,10 @@ extern "C"
                 return bail(MHB_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess)
             return bail(MHB_ERR_CUDA);
+        int prio_lo = 0, prio_hi = 0; // helper streams 0-1 (big-row bins) get the high priority
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         for (int a = 0; a < mhb_context::kAux; ++a)
-            if (cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking) != cudaSuccess ||
+            if (cudaStreamCreateWithPriority(&h->aux[a], cudaStreamNonBlocking, a < 2 ? prio_hi : prio_lo) != cudaSuccess ||
                 cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming) != cudaSuccess)
                 return bail(MHB_ERR_CUDA);
         if (set_kernel_attributes(h) != MHB_OK)
