@@ -509,7 +509,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, NB_WIN_WARP_COLS);
+               Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(NB_H_WARP_S)) > 0)
     {
@@ -527,7 +527,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
-               Cv, NB_WIN_G8_COLS);
+               Cv, NB_WIN_G8_COLS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(NB_H_G8)) > 0)
     {

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(kNumGroupThreads)
     k_num_win_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                     const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                     const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
-                    const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int wcap)
+                    const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int wcap,
+                    const unsigned char *__restrict__ same)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int GPB = kNumGroupThreads / G;
@@ -55,11 +56,12 @@ __global__ void __launch_bounds__(kNumGroupThreads)
             acc[i] = Unset<T>::value();
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        // the columns of one B row are distinct: plain read-modify-write, no atomics
-        walk_sequential<G, kPre, T, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
+        // the columns of one B row are distinct: plain read-modify-write, no atomics;
+        // twin B rows (same pattern, adjacent in A's row) are folded into one update
+        walk_sequential_twins<G, kPre, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, same, [&](int c, T v) {
             const int idx = c - cmin;
             const T o = acc[idx];
-            acc[idx] = Unset<T>::is(o) ? a * v : fma(a, v, o);
+            acc[idx] = Unset<T>::is(o) ? v : o + v;
         });
         // ordered compaction: the window is already sorted by column
         int out = __ldg(&Cp[row]);

@@ -115,6 +115,121 @@ __device__ __forceinline__ void walk_sequential(unsigned gm, int l, int s, int e
     }
 }
 
+// walk_sequential for the numeric pass with TWIN folding.  Multi-dof FEM matrices hold runs
+// of B rows with identical column patterns (same[k] = row k repeats row k-1, family 1), and
+// the nonzeros of A that select them sit next to each other.  Up to three such nonzeros are
+// consumed as one step: the columns are loaded once (from the first twin), the three value
+// rows are combined in registers, v = a0*b0 + a1*b1 + a2*b2, and the accumulator sees ONE
+// read-modify-write instead of three.  For the cant-like input this removes 2/3 of the
+// shared-memory traffic, which is what bounds the kernel (profiles/r1a_numwin_baseline.md:
+// LSU data pipe 59 %, 2-way bank conflicts on the fp64 window).
+// update(c, v): v already contains the A factor.
+template <int G, int kPre, typename T, class Update>
+__device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s, int e,
+                                                      const int *__restrict__ Ac, const T *__restrict__ Av,
+                                                      const int *__restrict__ Bp, const int *__restrict__ Bc,
+                                                      const T *__restrict__ Bv,
+                                                      const unsigned char *__restrict__ same, Update update)
+{
+    int bs, be, kk, nbs, nbe, nkk;
+    T av, nav;
+    auto meta = [&](int j, int &ms, int &me, int &mk, T &ma) {
+        ms = 0, me = 0, mk = -2, ma = T(0);
+        if (j < e)
+        {
+            mk = __ldg(&Ac[j]);
+            ma = __ldg(&Av[j]);
+            ms = __ldg(&Bp[mk]);
+            me = __ldg(&Bp[mk + 1]);
+            if (__ldg(&same[mk]))
+                mk |= 0x40000000;
+        }
+    };
+    meta(s + l, bs, be, kk, av);
+    for (int j0 = s; j0 < e; j0 += G)
+    {
+        meta(j0 + G + l, nbs, nbe, nkk, nav);
+        const int cnt = min(G, e - j0);
+        // follower = repeats the pattern of the nonzero just before it (inside this chunk)
+        const int kprev = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
+        const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
+        const unsigned fmask = (__ballot_sync(gm, fol) >> (lane_id() & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+        int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0;
+        T pv0[kPre], pv1[kPre], pv2[kPre], na0 = T(0), na1 = T(0), na2 = T(0);
+        // group starting at entry i: size 1 + (following follower bits, at most 2)
+        auto issue = [&](int i) {
+            nsz = 1 + ((fmask >> (i + 1)) & 1u);
+            if (nsz == 2)
+                nsz += (fmask >> (i + 2)) & 1u;
+            if (i + nsz > cnt)
+                nsz = cnt - i;
+            nq = __shfl_sync(gm, bs, i, G);
+            nqe = __shfl_sync(gm, be, i, G);
+            na0 = __shfl_sync(gm, av, i, G);
+            // twins: offsets of their value rows relative to the first twin's
+            nb1 = __shfl_sync(gm, bs, min(i + 1, G - 1), G) - nq;
+            nb2 = __shfl_sync(gm, bs, min(i + 2, G - 1), G) - nq;
+            na1 = __shfl_sync(gm, av, min(i + 1, G - 1), G);
+            na2 = __shfl_sync(gm, av, min(i + 2, G - 1), G);
+#pragma unroll
+            for (int t = 0; t < kPre; ++t)
+            {
+                const int p = nq + t * G + l;
+                pc[t] = -1;
+                if (p < nqe)
+                {
+                    pc[t] = __ldg(&Bc[p]);
+                    pv0[t] = __ldg(&Bv[p]);
+                    if (nsz > 1)
+                        pv1[t] = __ldg(&Bv[p + nb1]);
+                    if (nsz > 2)
+                        pv2[t] = __ldg(&Bv[p + nb2]);
+                }
+            }
+        };
+        issue(0);
+        for (int i = 0; i < cnt;)
+        {
+            int cc[kPre];
+            T cv[kPre];
+            const int q = nq, qe = nqe, sz = nsz, b1 = nb1, b2 = nb2;
+            const T a0 = na0, a1 = na1, a2 = na2;
+#pragma unroll
+            for (int t = 0; t < kPre; ++t)
+            {
+                cc[t] = pc[t];
+                if (cc[t] >= 0)
+                {
+                    T v = a0 * pv0[t];
+                    if (sz > 1)
+                        v = fma(a1, pv1[t], v);
+                    if (sz > 2)
+                        v = fma(a2, pv2[t], v);
+                    cv[t] = v;
+                }
+            }
+            i += sz;
+            if (i < cnt)
+                issue(i);
+#pragma unroll
+            for (int t = 0; t < kPre; ++t)
+                if (cc[t] >= 0)
+                    update(cc[t], cv[t]);
+            for (int p = q + kPre * G + l; p < qe; p += G) // B rows longer than kPre*G
+            {
+                T v = a0 * __ldg(&Bv[p]);
+                if (sz > 1)
+                    v = fma(a1, __ldg(&Bv[p + b1]), v);
+                if (sz > 2)
+                    v = fma(a2, __ldg(&Bv[p + b2]), v);
+                update(__ldg(&Bc[p]), v);
+            }
+            __syncwarp(gm); // order this step's stores before the next step's loads
+        }
+        bs = nbs, be = nbe, kk = nkk, av = nav;
+    }
+}
+
 // update(c, v, a) must be atomic with respect to the other lanes of the group.
 // Every group walks ALL chunks of G nonzeros of A (j0 = s, s + G, ...); the products of a
 // chunk are split between the `tparts` groups sharing the row: this group takes products
