@@ -34,7 +34,7 @@ constexpr int kPre = 3;      // chunks of the next B row prefetched by the dense
 // Dense window, G lanes per row.
 // =========================================================================================
 template <int G, typename T>
-__global__ void __launch_bounds__(kNumGroupThreads)
+__global__ void __launch_bounds__(kNumGroupThreads, 3) // 3 blocks/SM is what the 64 KB windows allow
     k_num_win_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                     const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                     const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
@@ -58,10 +58,12 @@ __global__ void __launch_bounds__(kNumGroupThreads)
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         // the columns of one B row are distinct: plain read-modify-write, no atomics;
         // twin B rows (same pattern, adjacent in A's row) are folded into one update
-        walk_sequential_twins<G, kPre, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, same, [&](int c, T v) {
-            const int idx = c - cmin;
+        walk_sequential_twins<G, kPre, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, same, [&](int c, T v, bool active) {
+            const int idx = active ? c - cmin : 0; // idle lanes read slot 0 (a broadcast) and store nothing
             const T o = acc[idx];
-            acc[idx] = Unset<T>::is(o) ? v : o + v;
+            const T nv = Unset<T>::is(o) ? v : o + v;
+            if (active)
+                acc[idx] = nv;
         });
         // ordered compaction: the window is already sorted by column
         int out = __ldg(&Cp[row]);

@@ -133,6 +133,7 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
 {
     int bs, be, kk, nbs, nbe, nkk;
     T av, nav;
+    const int gbase = lane_id() & ~(G - 1);
     auto meta = [&](int j, int &ms, int &me, int &mk, T &ma) {
         ms = 0, me = 0, mk = -2, ma = T(0);
         if (j < e)
@@ -153,7 +154,7 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
         // follower = repeats the pattern of the nonzero just before it (inside this chunk)
         const int kprev = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
         const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
-        const unsigned fmask = (__ballot_sync(gm, fol) >> (lane_id() & ~(G - 1))) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+        const unsigned fmask = (__ballot_sync(gm, fol) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
         int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0;
         T pv0[kPre], pv1[kPre], pv2[kPre], na0 = T(0), na1 = T(0), na2 = T(0);
         // group starting at entry i: size 1 + (following follower bits, at most 2)
@@ -197,24 +198,21 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
 #pragma unroll
             for (int t = 0; t < kPre; ++t)
             {
+                // lanes without an element compute on stale registers; their result is dropped
                 cc[t] = pc[t];
-                if (cc[t] >= 0)
-                {
-                    T v = a0 * pv0[t];
-                    if (sz > 1)
-                        v = fma(a1, pv1[t], v);
-                    if (sz > 2)
-                        v = fma(a2, pv2[t], v);
-                    cv[t] = v;
-                }
+                T v = a0 * pv0[t];
+                if (sz > 1)
+                    v = fma(a1, pv1[t], v);
+                if (sz > 2)
+                    v = fma(a2, pv2[t], v);
+                cv[t] = v;
             }
             i += sz;
             if (i < cnt)
                 issue(i);
 #pragma unroll
             for (int t = 0; t < kPre; ++t)
-                if (cc[t] >= 0)
-                    update(cc[t], cv[t]);
+                update(cc[t], cv[t], cc[t] >= 0); // predicated inside: no divergent region
             for (int p = q + kPre * G + l; p < qe; p += G) // B rows longer than kPre*G
             {
                 T v = a0 * __ldg(&Bv[p]);
@@ -222,7 +220,7 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
                     v = fma(a1, __ldg(&Bv[p + b1]), v);
                 if (sz > 2)
                     v = fma(a2, __ldg(&Bv[p + b2]), v);
-                update(__ldg(&Bc[p]), v);
+                update(__ldg(&Bc[p]), v, true);
             }
             __syncwarp(gm); // order this step's stores before the next step's loads
         }
