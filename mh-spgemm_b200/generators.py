@@ -129,15 +129,15 @@ def with_dense_rows(A: CSR, nrows: int, length: int, seed: int = 7) -> CSR:
 # name -> (constructor, kwargs): synthetic analogs of the 16matrix.txt suite shapes
 # (SURVEY.md section 8d targets in the comment: rows / nnz).
 SUITE = {
-    "pdb1HYS":          (fem3d, dict(nx=5, ny=5, nz=162, dof=9, seed=11)),      # 36,417 / 4.34M
-    "pwtk":             (fem3d, dict(nx=6, ny=6, nz=1009, dof=6, seed=12)),     # 217,918 / 11.6M
+    "pdb1HYS":          (fem3d, dict(nx=6, ny=6, nz=202, dof=5, seed=11)),      # 36,417 / 4.34M
+    "pwtk":             (fem3d, dict(nx=4, ny=4, nz=4540, dof=3, seed=12)),     # 217,918 / 11.6M
     "webbase-1M":       (rmat, dict(scale=20, n=1_000_005, draws=3_300_000, seed=2)),
     "cage12":           (banded_random, dict(M=130_228, per_row=15, halfband=3000, seed=13)),
     "cant":             (fem3d, dict(nx=8, ny=8, nz=325, dof=3, seed=1)),       # 62,451 / 4.0M
-    "hood":             (fem3d, dict(nx=12, ny=12, nz=510, dof=3, seed=14)),    # 220,542 / 10.8M
-    "rma10":            (fem3d, dict(nx=5, ny=5, nz=375, dof=5, seed=15)),      # 46,835 / 2.37M
-    "scircuit":         (rmat, dict(scale=18, n=170_998, draws=1_000_000, a=0.40, b=0.20, c=0.20, seed=16)),
-    "shipsec1":         (fem3d, dict(nx=8, ny=8, nz=367, dof=6, seed=17)),      # 140,874 / 7.8M
+    "hood":             (fem3d, dict(nx=3, ny=4, nz=6126, dof=3, seed=14)),     # 220,542 / 10.8M
+    "rma10":            (fem3d, dict(nx=4, ny=4, nz=976, dof=3, seed=15)),      # 46,835 / 2.37M
+    "scircuit":         (rmat, dict(scale=18, n=170_998, draws=1_700_000, a=0.40, b=0.20, c=0.20, seed=16)),
+    "shipsec1":         (fem3d, dict(nx=4, ny=4, nz=2935, dof=3, seed=17)),     # 140,874 / 7.8M
     "cop20k_A":         (banded_random, dict(M=121_192, per_row=21, halfband=20000, seed=18)),
     "mac_econ_fwd500":  (banded_random, dict(M=206_500, per_row=5, halfband=500, seed=19)),
     "offshore":         (banded_random, dict(M=259_789, per_row=15, halfband=5000, seed=20)),
