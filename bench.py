@@ -9,7 +9,10 @@ A "step" is one complete SpGEMM (B mask build, binning, symbolic, nnz hand-off +
 of C, numeric) with A and B already resident in HBM.  N=1 runs BASELINE.json configs[1]
 (the cant-like FEM matrix, 62,400 rows / 4.24 M nnz / 302.5 M products); N>1 runs the same
 per-GPU work on a matrix N times longer (weak scaling): A is row-sharded by
-intermediate-product count, B is broadcast from rank 0 with NCCL inside every step.
+intermediate-product count; inside every step B is exchanged with NCCL -- by default B is
+row-sharded like A and each rank gathers the row range of B its block references
+(--exchange range: a halo for FEM inputs, an all-gather for graphs), or B lives on rank 0
+and is broadcast (--exchange broadcast).
 
 `--impl reference` times the UNMODIFIED reference kernels rebuilt for sm_100
 (oracle/_ref, through MH_spgemm) on the same input; if that library is absent it times
@@ -52,8 +55,9 @@ def make_workload(name: str, scale: int = 1) -> tuple[CSR, dict]:
         A = G.fem3d(8, 8, 325 * scale, 3, seed=1)
         desc = f"configs[1] cant-like FEM 27-pt 8x8x{325 * scale} x3dof, C=A*A"
     elif name == "P":
-        A = G.poisson2d(256)
-        desc = "configs[0] Poisson 256x256 5-pt, C=A*A"
+        n = int(os.environ.get("MHB_POISSON_N", "256"))
+        A = G.poisson2d(n)
+        desc = f"configs[0] Poisson {n}x{n} 5-pt, C=A*A"
     elif name == "R":
         A = G.rmat()
         desc = "configs[2] webbase-like R-MAT scale 20, C=A*A"
@@ -185,6 +189,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="F", choices=["F", "P", "R"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="range", choices=["range", "broadcast"],
+                    help="N>1: 'range' = B row-sharded like A, each rank gathers the B rows its block "
+                         "references (halo for FEM, all-gather for graphs); 'broadcast' = B on rank 0, "
+                         "ncclBroadcast every step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +204,8 @@ def main():
     import torch
     import torch.distributed as dist
     from mh_spgemm_b200 import api
-    from mh_spgemm_b200.distributed import ShardedSpGEMM, pack_b, partition_rows, row_work
+    from mh_spgemm_b200.distributed import (RangeExchange, ShardedSpGEMM, column_range, pack_b, partition_rows,
+                                            row_work)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -220,13 +229,25 @@ def main():
     dt = torch.float64
     a_dev = (Ablk.M, torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
              torch.from_numpy(Ablk.val).to(dev))
-    packed, _ = pack_b(B)
-    Bbuf = packed.to(dev) if rank == 0 else torch.empty_like(packed, device=dev)
     sh = ShardedSpGEMM(tool, rank, world, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    use_range = world > 1 and args.exchange == "range"
+    if use_range:
+        kr = [column_range(A.rows(int(bounds[r]), int(bounds[r + 1]))) for r in range(world)]
+        plan = RangeExchange(rank, world, bounds, kr, B.ptr, dt, dev)
+        a_shift = (a_dev[0], a_dev[1], a_dev[2] - plan.k0, a_dev[3])
+        exch_bytes = plan.bytes_received
 
-    def one_step():
-        return sh.step(a_dev, Bbuf, B.M, B.N, B.nnz, dt, src=0)
+        def one_step():
+            # B = A is sharded like A: this rank's shard of B is its own block of A
+            return sh.step_range(a_shift, plan, a_dev[2], a_dev[3], B.N, dt)
+    else:
+        packed, _ = pack_b(B)
+        Bbuf = packed.to(dev) if rank == 0 else torch.empty_like(packed, device=dev)
+        exch_bytes = 0 if world == 1 else packed.numel()
+
+        def one_step():
+            return sh.step(a_dev, Bbuf, B.M, B.N, B.nnz, dt, src=0)
 
     for _ in range(args.warmup):
         out = one_step()
@@ -290,7 +311,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(cfg, intprod=intprod, nnzC=nnzC_total, l2="flushed between timed steps (256 MiB write)",
                            parallelism=("single GPU" if world == 1 else
-                                        f"A row-sharded x{world} by product count, B NCCL-broadcast each step")),
+                                        f"A row-sharded x{world} by product count; " +
+                                        ("B row-sharded like A, referenced row range gathered by NCCL send/recv "
+                                         "each step" if use_range else "B NCCL-broadcast from rank 0 each step")),
+                           exchange_bytes_received_rank0=exch_bytes),
             "roofline": {"bound": "hbm", "kernel": "numeric (k_num_win_group<32,double>)" if args.workload == "F"
                          else "numeric (all bins)", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,

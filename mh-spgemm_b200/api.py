@@ -216,6 +216,22 @@ class Tool:
         return CSR(A.M, B.N, view(cp, A.M + 1, np.int32), view(cc, n, np.int32), view(cv, n, dt))
 
     # -- device-resident phases (torch tensors own the memory) ----------------------------
+    def spgemm_sliced(self, A: CSR, B: CSR | None = None, cap: int = 2**31 - 1):
+        """C = A*B for products whose nnz(C) may exceed the int32 contract: A's rows are cut
+        into slices with at most `cap` intermediate products each (nnz(C slice) <= cap), every
+        slice is one SpGEMM with its own local int32 row_ptr, and the caller gets the slices
+        plus their int64 offsets.  Returns [(r0, r1, CSR slice)], offsets (int64)."""
+        from .distributed import row_work, slice_rows_fast
+        B = A if B is None else B
+        work = row_work(A, B)
+        out, offs, run = [], [], 0
+        for r0, r1 in slice_rows_fast(work, 0, A.M, cap):
+            C = self.spgemm_host(A.rows(r0, r1), B)
+            out.append((r0, r1, C))
+            offs.append(run)
+            run += C.nnz
+        return out, np.array(offs + [run], np.int64)
+
     def symbolic(self, M, K, N, dA_ptr, dA_col, dB_ptr, dB_col):
         """-> (dC_ptr int32[M+1], nnzC).  Inputs: int32 device arrays (DeviceArray or CUDA
         torch tensors -- anything with data_ptr()/numel())."""

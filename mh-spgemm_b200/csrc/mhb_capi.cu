@@ -120,6 +120,7 @@ struct mhb_context
     std::string err;
     // options
     int force_sym = 0, force_num = 0, verbose = 0;
+    long long nnz_limit = INT_MAX; // option "nnz_limit": lets tests exercise the int32-overflow path
     // problem of the last symbolic call
     bool have_pattern = false;
     int M = 0, K = 0, N = 0, nnzA = 0, nnzB = 0;
@@ -665,7 +666,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     h->timing.numeric_binning = ev_ms(h, EV_SYM, EV_NUMBIN);
     h->timing.malloc_C_col_val = ev_ms(h, EV_NUMBIN, EV_HANDOFF);
     h->timing.total = ev_ms(h, EV_START, EV_HANDOFF);
-    if (h->nnzC > (long long)INT_MAX)
+    if (h->nnzC > h->nnz_limit)
         return fail(h, MHB_ERR_OVERFLOW,
                     "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the int32 CSR contract; shard the rows of A");
     h->have_pattern = true;
@@ -913,6 +914,8 @@ extern "C"
             h->force_sym = (int)value;
         else if (k == "force_num_path")
             h->force_num = (int)value;
+        else if (k == "nnz_limit")
+            h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")
             h->serial = value != 0;
         else if (k == "verbose")

@@ -81,6 +81,8 @@ def exchange_B(Bbuf, world: int, src: int = 0):
 def slice_offsets(nnz_local: int, rank: int, world: int, device):
     """All-gather the per-rank nnz(C slice) (int64) -> (offset of this rank's slice in the
     global col/val arrays, total nnz(C))."""
+    if world == 1:
+        return 0, int(nnz_local)
     import torch
     import torch.distributed as dist
     mine = torch.tensor([nnz_local], dtype=torch.int64, device=device)
@@ -91,6 +93,72 @@ def slice_offsets(nnz_local: int, rank: int, world: int, device):
         allnnz = mine
     sizes = allnnz.cpu().numpy()
     return int(sizes[:rank].sum()), int(sizes.sum())
+
+
+class RangeExchange:
+    """B exchange when B is row-sharded like A (the natural layout for C = A*A): rank r owns
+    B rows [bounds[r], bounds[r+1]) and needs the rows [k0, k1) that the columns of its A
+    block reference.  Every step it receives the missing pieces of col/val from their
+    owners (grouped NCCL send/recv over NVLink) into one contiguous image of rows [k0, k1).
+    Banded / FEM inputs exchange only a halo; for graphs whose blocks reference all of B
+    this is an all-gather.  The row offsets of the gathered range depend only on the
+    pattern and are rebuilt once per plan."""
+
+    def __init__(self, rank, world, bounds, kranges, B_ptr_host, val_dtype, device):
+        import torch
+        self.rank, self.world, self.device = rank, world, device
+        bp = np.asarray(B_ptr_host, np.int64)
+        self.k0, self.k1 = int(kranges[rank][0]), int(kranges[rank][1])
+        self.K_local = self.k1 - self.k0
+        self.nnz_local = int(bp[self.k1] - bp[self.k0])
+        self.ptr = torch.from_numpy((bp[self.k0:self.k1 + 1] - bp[self.k0]).astype(np.int32)).to(device)
+        self.col = torch.empty(max(self.nnz_local, 1), dtype=torch.int32, device=device)
+        self.val = torch.empty(max(self.nnz_local, 1), dtype=val_dtype, device=device)
+        own0 = int(bp[bounds[rank]])
+        self.recv, self.send, self.local = [], [], None
+        for o in range(world):  # pieces I need, by owner
+            ra, rb = max(self.k0, int(bounds[o])), min(self.k1, int(bounds[o + 1]))
+            if ra >= rb:
+                continue
+            dst = (int(bp[ra] - bp[self.k0]), int(bp[rb] - bp[self.k0]))
+            if o == rank:
+                self.local = (int(bp[ra]) - own0, int(bp[rb]) - own0, dst[0], dst[1])
+            elif dst[1] > dst[0]:
+                self.recv.append((o, dst[0], dst[1]))
+        for d in range(world):  # pieces of mine that others need
+            if d == rank:
+                continue
+            ra, rb = max(int(kranges[d][0]), int(bounds[rank])), min(int(kranges[d][1]), int(bounds[rank + 1]))
+            if ra < rb and bp[rb] > bp[ra]:
+                self.send.append((d, int(bp[ra]) - own0, int(bp[rb]) - own0))
+        self.bytes_received = sum(b - a for _, a, b in self.recv) * (4 + torch.tensor([], dtype=val_dtype).element_size())
+
+    def run(self, own_col, own_val):
+        """own_col / own_val: this rank's shard of B (device).  Returns (ptr, col, val) of B
+        rows [k0, k1); A's column indices must be shifted by -k0 (done once by the caller)."""
+        import torch.distributed as dist
+        ops = []
+        for d, a, b in self.send:
+            ops.append(dist.P2POp(dist.isend, own_col[a:b], d))
+            ops.append(dist.P2POp(dist.isend, own_val[a:b], d))
+        for o, a, b in self.recv:
+            ops.append(dist.P2POp(dist.irecv, self.col[a:b], o))
+            ops.append(dist.P2POp(dist.irecv, self.val[a:b], o))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if self.local is not None:
+            sa, sb, da, db = self.local
+            self.col[da:db].copy_(own_col[sa:sb])
+            self.val[da:db].copy_(own_val[sa:sb])
+        for r in reqs:
+            r.wait()
+        return self.ptr, self.col, self.val
+
+
+def column_range(A: CSR) -> tuple[int, int]:
+    """[k0, k1): rows of B referenced by the columns of A (the halo-aware exchange range)."""
+    if A.nnz == 0:
+        return 0, 0
+    return int(A.col.min()), int(A.col.max()) + 1
 
 
 class ShardedSpGEMM:
@@ -116,6 +184,47 @@ class ShardedSpGEMM:
         self.tool.numeric_into(av, bv, ccol, cval)
         off, total = slice_offsets(nnz, self.rank, self.world, self.device)
         return cp, ccol[:nnz], cval[:nnz], off, total
+
+    def step_range(self, A_blk_shifted, plan: RangeExchange, own_col, own_val, N: int, val_dtype):
+        """Same as step() with B row-sharded like A: gather the referenced row range of B
+        (RangeExchange), multiply the local block (whose columns were shifted by -k0)."""
+        import torch
+        bp, bc, bv = plan.run(own_col, own_val)
+        Ml, ap, ac, av = A_blk_shifted
+        cp, nnz = self.tool.symbolic(Ml, plan.K_local, N, ap, ac, bp, bc[:plan.nnz_local])
+        ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
+        cval = torch.empty(max(nnz, 1), dtype=val_dtype, device=self.device)
+        self.tool.numeric_into(av, bv, ccol, cval)
+        off, total = slice_offsets(nnz, self.rank, self.world, self.device)
+        return cp, ccol[:nnz], cval[:nnz], off, total
+
+
+def slice_rows_by_products(work: np.ndarray, r0: int, r1: int, cap: int = 2**31 - 1) -> list[tuple[int, int]]:
+    """Cut rows [r0, r1) into consecutive slices whose intermediate-product sums stay <= cap.
+    nnz(C slice) <= products(slice), so every slice honours the int32 CSR contract
+    (SURVEY.md 'int32 limits': C of the 16 M-row R-MAT exceeds 2^31 entries)."""
+    out, start, acc = [], r0, 0
+    for r in range(r0, r1):
+        w = int(work[r])
+        if acc + w > cap and r > start:
+            out.append((start, r))
+            start, acc = r, 0
+        acc += w
+    out.append((start, r1))
+    return out
+
+
+def slice_rows_fast(work: np.ndarray, r0: int, r1: int, cap: int = 2**31 - 1) -> list[tuple[int, int]]:
+    """Vectorised version of slice_rows_by_products (greedy cuts via searchsorted)."""
+    pre = np.concatenate([[0], np.cumsum(work[r0:r1], dtype=np.int64)])
+    out, start = [], 0
+    n = r1 - r0
+    while start < n:
+        end = int(np.searchsorted(pre, pre[start] + cap, side="right")) - 1
+        end = min(max(end, start + 1), n)
+        out.append((r0 + start, r0 + end))
+        start = end
+    return out or [(r0, r1)]
 
 
 def concat_slices(slices):

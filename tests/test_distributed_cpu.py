@@ -70,13 +70,30 @@ def _worker(rank, world, port, q):
     off, total = D.slice_offsets(int(Cp[-1]), rank, world, torch.device("cpu"))
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((Cp, Cc, Cv, off, total), gathered, dst=0)
+    # second layout: B row-sharded like A, halo-aware range exchange (send/recv)
+    F = G.fem3d(3, 3, 40, 2, seed=6)
+    fb = D.partition_rows(D.row_work(F, F), world)
+    kr = [D.column_range(F.rows(int(fb[r]), int(fb[r + 1]))) for r in range(world)]
+    plan = D.RangeExchange(rank, world, fb, kr, F.ptr, torch.float64, torch.device("cpu"))
+    lo, hi = int(F.ptr[fb[rank]]), int(F.ptr[fb[rank + 1]])
+    bp2, bc2, bv2 = plan.run(torch.from_numpy(F.col[lo:hi].copy()), torch.from_numpy(F.val[lo:hi].copy()))
+    fblk = F.rows(int(fb[rank]), int(fb[rank + 1]))
+    shifted = CSR(fblk.M, plan.K_local, fblk.ptr, fblk.col - plan.k0, fblk.val)
+    Bl2 = CSR(plan.K_local, F.N, bp2.numpy(), bc2.numpy()[:plan.nnz_local], bv2.numpy()[:plan.nnz_local])
+    Rp, Rc, Rv = orc.spgemm(shifted, Bl2)
+    gathered2 = [None] * world if rank == 0 else None
+    dist.gather_object((Rp, Rc, Rv, plan.bytes_received), gathered2, dst=0)
     if rank == 0:
         fp, fc, fv = orc.spgemm(A, B)
         gp, gc, gv = D.concat_slices([(g[0], g[1], g[2]) for g in gathered])
         ok = (np.array_equal(gp, fp) and np.array_equal(gc, fc) and np.array_equal(gv, fv)
               and all(g[4] == int(fp[-1]) for g in gathered)
               and [g[3] for g in gathered] == [int(fp[bounds[r]]) for r in range(world)])
-        q.put(bool(ok))
+        hp, hc, hv = orc.spgemm(F, F)
+        rp, rc, rv = D.concat_slices([(g[0], g[1], g[2]) for g in gathered2])
+        ok2 = np.array_equal(rp, hp) and np.array_equal(rc, hc) and np.array_equal(rv, hv)
+        halo_only = sum(g[3] for g in gathered2) < 0.5 * 12 * F.nnz  # far less than all of B
+        q.put(bool(ok and ok2 and halo_only))
     dist.destroy_process_group()
 
 
@@ -92,3 +109,15 @@ def test_world2_gloo_sharded_flow():
         p.join(240)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_slice_rows_respects_cap():
+    rng = np.random.default_rng(0)
+    w = rng.integers(0, 50, 1000).astype(np.int64)
+    for cap in (60, 500, 10**9):
+        a = D.slice_rows_by_products(w, 0, 1000, cap)
+        b = D.slice_rows_fast(w, 0, 1000, cap)
+        assert a == b
+        assert a[0][0] == 0 and a[-1][1] == 1000 and all(x[1] == y[0] for x, y in zip(a, a[1:]))
+        for r0, r1 in a:
+            assert w[r0:r1].sum() <= cap or r1 - r0 == 1

@@ -262,3 +262,31 @@ def test_row_sharded_slices_concatenate(tool, orc):
     gp, gc, gv = D.concat_slices(slices)
     assert np.array_equal(gp, full.ptr.astype(np.int64)) and np.array_equal(gc, full.col)
     np.testing.assert_allclose(gv, full.val, rtol=1e-12, atol=0)
+
+
+def test_sliced_product_for_int32_overflow(tool, orc):
+    """nnz(C) beyond int32 is handled by row slices with local int32 row_ptr and int64 slice
+    offsets; exercised here with an artificially small cap."""
+    from mh_spgemm_b200 import distributed as D
+    A = G.fem3d(4, 4, 30, 3, seed=8)
+    slices, offs = tool.spgemm_sliced(A, A, cap=200_000)
+    assert len(slices) > 3
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    gp, gc, gv = D.concat_slices([(c.ptr, c.col, c.val) for _, _, c in slices])
+    assert np.array_equal(gp, Cp) and np.array_equal(gc, Cc)
+    assert np.array_equal(offs, Cp[[s[0] for s in slices] + [A.M]])
+    np.testing.assert_allclose(gv, Cv, rtol=1e-12, atol=0)
+
+
+def test_overflow_is_reported_not_truncated():
+    """nnz(C) above the int32 contract (simulated with the nnz_limit knob) is a status, and
+    the handle stays usable."""
+    t = api.Tool(0)
+    A = G.poisson2d(24)
+    t.set_option("nnz_limit", 100)
+    with pytest.raises(api.MhbError) as e:
+        t.spgemm_host(A, A)
+    assert e.value.code == 3 and "shard" in str(e.value)
+    t.set_option("nnz_limit", 0)
+    assert t.spgemm_host(A, A).nnz > 100
+    t.release()
