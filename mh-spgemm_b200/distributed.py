@@ -78,9 +78,10 @@ def exchange_B(Bbuf, world: int, src: int = 0):
     return Bbuf
 
 
-def slice_offsets(nnz_local: int, rank: int, world: int, device):
+def slice_offsets(nnz_local: int, rank: int, world: int, device, on_host: bool = True):
     """All-gather the per-rank nnz(C slice) (int64) -> (offset of this rank's slice in the
-    global col/val arrays, total nnz(C))."""
+    global col/val arrays, total nnz(C)).  on_host=False returns 0-dim device tensors and
+    does not synchronise (the step then ends without a host round trip)."""
     if world == 1:
         return 0, int(nnz_local)
     import torch
@@ -91,6 +92,8 @@ def slice_offsets(nnz_local: int, rank: int, world: int, device):
         dist.all_gather_into_tensor(allnnz, mine)
     else:
         allnnz = mine
+    if not on_host:
+        return allnnz[:rank].sum(), allnnz.sum()
     sizes = allnnz.cpu().numpy()
     return int(sizes[:rank].sum()), int(sizes.sum())
 
@@ -133,6 +136,12 @@ class RangeExchange:
                 self.send.append((d, int(bp[ra]) - own0, int(bp[rb]) - own0))
         self.bytes_received = sum(b - a for _, a, b in self.recv) * (4 + torch.tensor([], dtype=val_dtype).element_size())
 
+    def own_views(self):
+        """Views of this rank's own shard INSIDE the gathered image.  A caller that keeps its
+        shard of B there (instead of in separate arrays) saves the local copy of run()."""
+        sa, sb, da, db = self.local
+        return self.col[da:db], self.val[da:db]
+
     def run(self, own_col, own_val):
         """own_col / own_val: this rank's shard of B (device).  Returns (ptr, col, val) of B
         rows [k0, k1); A's column indices must be shifted by -k0 (done once by the caller)."""
@@ -147,8 +156,9 @@ class RangeExchange:
         reqs = dist.batch_isend_irecv(ops) if ops else []
         if self.local is not None:
             sa, sb, da, db = self.local
-            self.col[da:db].copy_(own_col[sa:sb])
-            self.val[da:db].copy_(own_val[sa:sb])
+            if own_col.data_ptr() != self.col[da:db].data_ptr():  # shard not already in place
+                self.col[da:db].copy_(own_col[sa:sb])
+                self.val[da:db].copy_(own_val[sa:sb])
         for r in reqs:
             r.wait()
         return self.ptr, self.col, self.val
@@ -182,10 +192,11 @@ class ShardedSpGEMM:
         ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
         cval = torch.empty(max(nnz, 1), dtype=val_dtype, device=self.device)
         self.tool.numeric_into(av, bv, ccol, cval)
-        off, total = slice_offsets(nnz, self.rank, self.world, self.device)
+        off, total = slice_offsets(nnz, self.rank, self.world, self.device, on_host=True)
         return cp, ccol[:nnz], cval[:nnz], off, total
 
-    def step_range(self, A_blk_shifted, plan: RangeExchange, own_col, own_val, N: int, val_dtype):
+    def step_range(self, A_blk_shifted, plan: RangeExchange, own_col, own_val, N: int, val_dtype,
+                   offsets_on_host: bool = True):
         """Same as step() with B row-sharded like A: gather the referenced row range of B
         (RangeExchange), multiply the local block (whose columns were shifted by -k0)."""
         import torch
@@ -195,7 +206,7 @@ class ShardedSpGEMM:
         ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
         cval = torch.empty(max(nnz, 1), dtype=val_dtype, device=self.device)
         self.tool.numeric_into(av, bv, ccol, cval)
-        off, total = slice_offsets(nnz, self.rank, self.world, self.device)
+        off, total = slice_offsets(nnz, self.rank, self.world, self.device, on_host=offsets_on_host)
         return cp, ccol[:nnz], cval[:nnz], off, total
 
 
