@@ -24,9 +24,9 @@ from .csr import CSR
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
-SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL"]
+SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [

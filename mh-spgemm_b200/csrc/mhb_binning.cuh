@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
     {
         n = counts[i];
         int4 info = arow[i];
-        binid[i] = (unsigned char)mhb_classify_num(n, info.z, info.w, force_path);
+        binid[i] = (unsigned char)mhb_classify_num(n, info.x, info.z, info.w, force_path);
     }
     __shared__ int sh_mx[8];
     n = group_max<32>(n, kFull);

@@ -435,6 +435,12 @@ int launch_symbolic_bins(mhb_context *h)
                GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                SB_BM_G8_WORDS, h->bsame.as<unsigned char>());
     }
+    if ((n = n_of(SB_TINY)) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, bins + off[SB_TINY], n,
+                  h->Ap, h->Ac, tp, tc, tm, counts);
+    }
     return join_bins(h);
 }
 
@@ -538,6 +544,12 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal);
+    }
+    if ((n = n_of(NB_TINY)) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads, 0,
+                  bins + off[NB_TINY], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
     }
     return join_bins(h);
 }

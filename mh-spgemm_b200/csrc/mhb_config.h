@@ -28,6 +28,7 @@ enum MhbSymBin
     SB_H_BLOCK_S,   // tile hash, block/row,   ub <= 3072 (4096 slots)
     SB_H_BLOCK_L,   // tile hash, block/row,   ub <= 12288 (16384 slots)
     SB_H_GLOBAL,    // tile hash in global memory
+    SB_TINY,        // one thread per row, tile list in shared memory, tile-flop <= 24
     SB_COUNT
 };
 #define SB_BM_G8_WORDS 64
@@ -41,6 +42,7 @@ enum MhbSymBin
 #define SB_H_BLOCK_S_MAX 3072
 #define SB_H_BLOCK_L_SLOTS 16384
 #define SB_H_BLOCK_L_MAX 12288
+#define SB_TINY_MAX 24
 #define SB_BITMAP_WORK_FACTOR 8 // bitmap when Wt <= 8 * tile-flop (or Wt <= 64)
 
 // ---- numeric bins (family 4). W = column span of the C row, n = nnz of the C row ----
@@ -57,6 +59,7 @@ enum MhbNumBin
     NB_H_BLOCK_S,   // hash, block/row,   n <= 2560 (4096 slots)
     NB_H_BLOCK_L,   // hash, block/row,   n <= 10240 (16384 slots)
     NB_H_GLOBAL,    // hash in global memory
+    NB_TINY,        // one thread per row, n <= 16 and <= 128 products
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -73,6 +76,8 @@ enum MhbNumBin
 #define NB_H_BLOCK_S_MAX 2560
 #define NB_H_BLOCK_L_SLOTS 16384
 #define NB_H_BLOCK_L_MAX 10240
+#define NB_TINY_MAX 16
+#define NB_TINY_PRODUCTS 128
 #define NB_WINDOW_WORK_FACTOR 32 // window when W <= 32 * n (or W <= 64)
 
 // path forcing (mhb_set_option "force_sym_path"/"force_num_path")
@@ -91,6 +96,8 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
 {
     if (ip <= 0)
         return SB_EMPTY;
+    if (force == MHB_PATH_AUTO && tf <= SB_TINY_MAX)
+        return SB_TINY;
     long long wt = (long long)(cmax >> MHB_TILE_SHIFT) - (cmin >> MHB_TILE_SHIFT) + 1;
     bool fits = wt <= SB_BM_BLOCK_WORDS;
     bool dense = fits && (wt <= SB_BM_G8_WORDS || wt <= (long long)SB_BITMAP_WORK_FACTOR * tf);
@@ -113,10 +120,12 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
 }
 
 // Row metrics -> numeric bin.  n = nnz of the C row.
-MHB_HD int mhb_classify_num(int n, int cmin, int cmax, int force)
+MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force)
 {
     if (n <= 0)
         return NB_EMPTY;
+    if (force == MHB_PATH_AUTO && n <= NB_TINY_MAX && ip <= NB_TINY_PRODUCTS)
+        return NB_TINY;
     long long w = (long long)cmax - cmin + 1;
     bool fits = w <= NB_WIN_BLOCK_L_COLS;
     bool dense = fits && (w <= 64 || w <= (long long)NB_WINDOW_WORK_FACTOR * n);

@@ -296,4 +296,53 @@ __global__ void __launch_bounds__(kSymThreads)
     }
 }
 
+// ---- tiny rows: one thread per row ------------------------------------------------------
+// Rows with at most SB_TINY_MAX tile visits (stencils, road networks, the bulk of power-law
+// rows).  A group of lanes per row spends most of its instructions on shuffles, table
+// initialisation and reductions for a dozen tiles; here a thread keeps the row's (tile,
+// mask) list in its own shared-memory column (slot j of thread t at [j*blockDim + t]: bank
+// = t, conflict-free whatever j each lane is at) and scans it linearly.
+constexpr int kTinyThreads = 256;
+
+__global__ void __launch_bounds__(kTinyThreads)
+    k_sym_tiny(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap, const int *__restrict__ Ac,
+               const int *__restrict__ tileptr, const int *__restrict__ tilecol,
+               const unsigned *__restrict__ tilemask, int *__restrict__ counts)
+{
+    __shared__ int keys[SB_TINY_MAX * kTinyThreads];
+    __shared__ unsigned masks[SB_TINY_MAX * kTinyThreads];
+    const int t = threadIdx.x;
+    for (int r = blockIdx.x * kTinyThreads + t; r < nrows; r += gridDim.x * kTinyThreads)
+    {
+        const int row = rows[r];
+        int n = 0;
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        for (int j = s; j < e; ++j)
+        {
+            const int k = __ldg(&Ac[j]);
+            const int qs = __ldg(&tileptr[k]), qe = __ldg(&tileptr[k + 1]);
+            for (int q = qs; q < qe; ++q)
+            {
+                const int tc = __ldg(&tilecol[q]);
+                const unsigned m = __ldg(&tilemask[q]);
+                int p = 0;
+                while (p < n && keys[p * kTinyThreads + t] != tc)
+                    ++p;
+                if (p < n)
+                    masks[p * kTinyThreads + t] |= m;
+                else
+                {
+                    keys[n * kTinyThreads + t] = tc;
+                    masks[n * kTinyThreads + t] = m;
+                    ++n;
+                }
+            }
+        }
+        int c = 0;
+        for (int p = 0; p < n; ++p)
+            c += __popc(masks[p * kTinyThreads + t]);
+        counts[row] = c;
+    }
+}
+
 } // namespace mhb
