@@ -290,3 +290,49 @@ def test_overflow_is_reported_not_truncated():
     t.set_option("nnz_limit", 0)
     assert t.spgemm_host(A, A).nnz > 100
     t.release()
+
+
+def test_cli_driver_matches_reference_report(tmp_path, orc):
+    """`spgemm <file.mtx>` equivalent (src/main.cu:74-217): same report lines, right nnz, and
+    the AAT mode (A * A^T through the host transpose of src/utils.cpp:20-46)."""
+    from mh_spgemm_b200.mmio import read_mtx, write_mtx
+    A = G.uniform_random(300, 200, 2500, seed=3)
+    sq = G.fem3d(3, 3, 8, 2, seed=4)
+    pa, ps = tmp_path / "rect.mtx", tmp_path / "fem.mtx"
+    write_mtx(str(pa), A)
+    write_mtx(str(ps), sq, symmetric_lower=False)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    run = lambda *a: subprocess.run([sys.executable, "-m", "mh_spgemm_b200.cli", *a], capture_output=True,  # noqa: E731
+                                    text=True, timeout=300, env=env, cwd=ROOT)
+    p = run(str(ps), "--out", str(tmp_path / "c.mtx"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    Cp, Cc, Cv = orc.spgemm(sq, sq)
+    assert f"C.nnz = {Cp[-1]}" in p.stdout and f"SpGEMM intermediate result = {orc.intprod(sq, sq)}" in p.stdout
+    assert "MH-SpGEMM runtime is" in p.stdout and "Gflops is" in p.stdout and "calculate_C_nnz" in p.stdout
+    C, _ = read_mtx(str(tmp_path / "c.mtx"))
+    assert np.array_equal(C.ptr, Cp) and np.array_equal(C.col, Cc)
+    np.testing.assert_allclose(C.val, Cv, rtol=1e-12)
+    p = run(str(pa))
+    assert "C=AA must have rowA = colA. Exit." in p.stdout
+    p = run(str(pa), "--aat")
+    Tp, _, _ = orc.spgemm(A, A.transpose())
+    assert p.returncode == 0 and f"C.nnz = {Tp[-1]}" in p.stdout
+
+
+def test_cusparse_cross_check():
+    """Third oracle: cuSPARSE SpGEMM driven exactly as the reference drives
+    it (inc/cusparse_spgemm.cuh:30-88, through oracle/_ref); its rows are compared as sorted
+    (col, val) sets because cuSPARSE does not promise column order."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libmhref.so")):
+        pytest.skip("oracle/_ref not built")
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import mh_spgemm_b200\n"
+        "from mh_spgemm_b200 import api, generators as G; from oracle import Reference\n"
+        "A = G.rmat(13, 8000, 40000, seed=12)\n"
+        "C = api.Tool(0).spgemm_host(A, A); R = Reference().cusparse(A, A)\n"
+        "assert R['nnz'] == C.nnz and np.array_equal(R['ptr'], C.ptr)\n"
+        "rows = np.repeat(np.arange(A.M), np.diff(C.ptr)); o = np.lexsort((R['col'], rows))\n"
+        "assert np.array_equal(R['col'][o], C.col)\n"
+        "np.testing.assert_allclose(R['val'][o], C.val, rtol=1e-12, atol=0); print('CUSPARSE-OK', C.nnz)\n" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CUSPARSE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
