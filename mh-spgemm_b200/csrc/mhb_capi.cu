@@ -518,6 +518,15 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
                GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
     }
+    if ((n = n_of(NB_H_WARP_M)) > 0)
+    {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+    }
     if ((n = n_of(NB_H_WARP_S)) > 0)
     {
         constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -526,6 +535,15 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+    }
+    if ((n = n_of(NB_H_WARP_XS)) > 0)
+    {
+        constexpr int G = 32, GPB = kNumGroupThreads / G;
+        auto kern = k_num_hash_group<G, T>;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+               GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
     }
     if ((n = n_of(NB_WIN_G8)) > 0)
     {

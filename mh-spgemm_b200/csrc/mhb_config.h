@@ -60,6 +60,8 @@ enum MhbNumBin
     NB_H_BLOCK_L,   // hash, block/row,   n <= 10240 (16384 slots)
     NB_H_GLOBAL,    // hash in global memory
     NB_TINY,        // one thread per row, n <= 16 and <= 128 products
+    NB_H_WARP_XS,   // hash, warp/row,    n <= 80  (128 slots)
+    NB_H_WARP_M,    // hash, warp/row,    n <= 320 (512 slots)
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -68,6 +70,10 @@ enum MhbNumBin
 #define NB_WIN_BLOCK_L_COLS 27648
 #define NB_H_G8_SLOTS 32
 #define NB_H_G8_MAX 24
+#define NB_H_WARP_XS_SLOTS 128
+#define NB_H_WARP_XS_MAX 80
+#define NB_H_WARP_M_SLOTS 512
+#define NB_H_WARP_M_MAX 320
 #define NB_H_WARP_S_SLOTS 256
 #define NB_H_WARP_S_MAX 160
 #define NB_H_WARP_L_SLOTS 1024
@@ -143,8 +149,12 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force)
     }
     if (n <= NB_H_G8_MAX)
         return NB_H_G8;
+    if (n <= NB_H_WARP_XS_MAX)
+        return NB_H_WARP_XS;
     if (n <= NB_H_WARP_S_MAX)
         return NB_H_WARP_S;
+    if (n <= NB_H_WARP_M_MAX)
+        return NB_H_WARP_M;
     if (n <= NB_H_WARP_L_MAX)
         return NB_H_WARP_L;
     if (n <= NB_H_BLOCK_S_MAX)

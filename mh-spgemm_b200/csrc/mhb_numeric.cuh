@@ -274,12 +274,14 @@ __device__ __forceinline__ bool bucket_sort_emit_warp(int *keys, T *vals, int n,
         atomicAdd(&start[(keys[i] - cmin) >> sh], 1);
     __syncwarp();
     // exclusive scan of the NB counts: lane l owns NB/32 consecutive buckets (NB >= 32)
-    const int per = NB >> 5; // 1 (S = 256) or 4 (S = 1024)
+    // lane l owns `per` consecutive buckets (NB = 16 .. 128: per = 1, 1, 2, 4; lanes >= NB idle)
+    const int per = max(NB >> 5, 1);
     int cnt[4], tot = 0, mx = 0;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
     {
-        cnt[t] = (t < per) ? start[l * per + t] : 0;
+        const int b = l * per + t;
+        cnt[t] = (t < per && b < NB) ? start[b] : 0;
         tot += cnt[t];
         mx = max(mx, cnt[t]);
     }
@@ -297,11 +299,14 @@ __device__ __forceinline__ bool bucket_sort_emit_warp(int *keys, T *vals, int n,
     int run = incl - tot;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-        if (t < per)
+    {
+        const int b = l * per + t;
+        if (t < per && b < NB)
         {
-            start[l * per + t] = run;
+            start[b] = run;
             run += cnt[t];
         }
+    }
     if (l == 31)
         start[NB] = n;
     __syncwarp();

@@ -336,3 +336,33 @@ def test_cusparse_cross_check():
         "np.testing.assert_allclose(R['val'][o], C.val, rtol=1e-12, atol=0); print('CUSPARSE-OK', C.nnz)\n" % ROOT)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "CUSPARSE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_global_memory_fallbacks_wide_matrix(tool, orc):
+    """Columns beyond the 1.8 M that a shared-memory bitmap covers and rows beyond the largest
+    shared-memory tables: the symbolic tile hash and the numeric hash both run from the
+    global-memory pool (the reference's 'global row' paths, inc/MH_spgemm.cuh:254-260,376-393)."""
+    rng = np.random.default_rng(5)
+    K, N = 48, 3_000_000
+    cols = np.concatenate([np.sort(rng.choice(N, 20_000, replace=False)) for _ in range(K)])
+    B = CSR(K, N, np.arange(K + 1) * 20_000, cols, rng.random(cols.size) + 0.5)
+    A = CSR(6, K, np.arange(7) * K, np.tile(np.arange(K), 6), rng.random(6 * K) + 0.5)
+    C = tool.spgemm_host(A, B)
+    st = tool.stats
+    assert st["sym_bins"]["H_GLOBAL"] == 6 and st["num_bins"]["H_GLOBAL"] == 6
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    assert_matches(orc, C, Cp, Cc, Cv)
+
+
+@pytest.mark.parametrize("shape", [(0, 5, 5), (5, 0, 5), (4, 4, 1), (1, 1, 1)])
+def test_degenerate_shapes(tool, orc, shape):
+    M, K, N = shape
+    rng = np.random.default_rng(1)
+    def rnd(m, n):
+        if m == 0 or n == 0:
+            return CSR(m, n, np.zeros(m + 1, np.int32), [], [])
+        return G.uniform_random(m, n, max(1, m * n // 2), seed=int(rng.integers(1 << 30)))
+    A, B = rnd(M, K), rnd(K, N)
+    C = tool.spgemm_host(A, B)
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    assert_matches(orc, C, Cp, Cc, Cv)
