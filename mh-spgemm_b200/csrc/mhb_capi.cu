@@ -515,7 +515,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_WIN_WARP_COLS * sizeof(T), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+               GPB * (NB_WIN_WARP_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(NB_H_WARP_M)) > 0)
@@ -551,7 +551,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_WIN_G8_COLS * sizeof(T), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
+               GPB * (NB_WIN_G8_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
                Cv, NB_WIN_G8_COLS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(NB_H_G8)) > 0)
@@ -577,10 +577,10 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_sym_bitmap_group<32>, 8 * SB_BM_WARP_WORDS * 4));
     CU(allow_smem(k_sym_bitmap_block, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_sym_hash_block, 2 * SB_H_BLOCK_L_SLOTS * 4));
-    CU(allow_smem(k_num_win_group<8, double>, 32 * NB_WIN_G8_COLS * 8));
-    CU(allow_smem(k_num_win_group<32, double>, 8 * NB_WIN_WARP_COLS * 8));
-    CU(allow_smem(k_num_win_group<8, float>, 32 * NB_WIN_G8_COLS * 4));
-    CU(allow_smem(k_num_win_group<32, float>, 8 * NB_WIN_WARP_COLS * 4));
+    CU(allow_smem(k_num_win_group<8, double>, 32 * (NB_WIN_G8_COLS * 8 + 160)));
+    CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
+    CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
+    CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
     CU(allow_smem(k_num_win_block<double>, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_num_win_block<float>, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_num_hash_group<32, double>, 8 * NB_H_WARP_L_SLOTS * 12));

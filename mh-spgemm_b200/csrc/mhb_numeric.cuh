@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kNumGroupThreads, 3) // 3 blocks/SM is what th
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     T *acc = reinterpret_cast<T *>(sm_raw) + (size_t)g * wcap;
+    // per-group staging of the current chunk of A's row (G + 2 int4), after all the windows
+    int4 *stage = reinterpret_cast<int4 *>(reinterpret_cast<T *>(sm_raw) + (size_t)GPB * wcap) + (size_t)g * (G + 2);
     for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
     {
         const int row = rows[r];
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(kNumGroupThreads, 3) // 3 blocks/SM is what th
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         // the columns of one B row are distinct: plain read-modify-write, no atomics;
         // twin B rows (same pattern, adjacent in A's row) are folded into one update
-        walk_sequential_twins<G, kPre, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, same, [&](int c, T v, bool active) {
+        walk_sequential_twins<G, kPre, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, same, stage, [&](int c, T v, bool active) {
             const int idx = active ? c - cmin : 0; // idle lanes read slot 0 (a broadcast) and store nothing
             const T o = acc[idx];
             const T nv = Unset<T>::is(o) ? v : o + v;

@@ -124,12 +124,38 @@ __device__ __forceinline__ void walk_sequential(unsigned gm, int l, int s, int e
 // shared-memory traffic, which is what bounds the kernel (profiles/r1a_numwin_baseline.md:
 // LSU data pipe 59 %, 2-way bank conflicts on the fp64 window).
 // update(c, v): v already contains the A factor.
+template <typename T>
+__device__ __forceinline__ int4 pack_meta(int bs, int be, T av)
+{
+    if constexpr (sizeof(T) == 8)
+    {
+        const long long bits = __double_as_longlong((double)av);
+        return make_int4(bs, be, (int)(bits & 0xffffffffLL), (int)(bits >> 32));
+    }
+    else
+        return make_int4(bs, be, __float_as_int((float)av), 0);
+}
+template <typename T>
+__device__ __forceinline__ T meta_val(const int4 &m)
+{
+    if constexpr (sizeof(T) == 8)
+        return (T)__longlong_as_double(((long long)m.w << 32) | (unsigned)m.z);
+    else
+        return (T)__int_as_float(m.z);
+}
+
+// `stage`: G + 2 int4 of shared memory owned by this group.  The per-nonzero metadata of the
+// current chunk of A ({B-row start, end, A value}) is parked there once per chunk and read
+// back with one broadcast LDS.128 per twin -- the first version fetched it with 11 shuffles
+// per step, and shuffles travel the same data pipe as the accumulator traffic that bounds
+// this kernel (profiles/r1b_numwin_twins.md).
 template <int G, int kPre, typename T, class Update>
 __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s, int e,
                                                       const int *__restrict__ Ac, const T *__restrict__ Av,
                                                       const int *__restrict__ Bp, const int *__restrict__ Bc,
                                                       const T *__restrict__ Bv,
-                                                      const unsigned char *__restrict__ same, Update update)
+                                                      const unsigned char *__restrict__ same, int4 *stage,
+                                                      Update update)
 {
     int bs, be, kk, nbs, nbe, nkk;
     T av, nav;
@@ -147,14 +173,18 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
         }
     };
     meta(s + l, bs, be, kk, av);
+    if (l < 2)
+        stage[G + l] = make_int4(0, 0, 0, 0);
     for (int j0 = s; j0 < e; j0 += G)
     {
         meta(j0 + G + l, nbs, nbe, nkk, nav);
         const int cnt = min(G, e - j0);
+        stage[l] = pack_meta<T>(bs, be, av);
         // follower = repeats the pattern of the nonzero just before it (inside this chunk)
         const int kprev = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
         const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
         const unsigned fmask = (__ballot_sync(gm, fol) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+        __syncwarp(gm); // stage[] visible to the group
         int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0;
         T pv0[kPre], pv1[kPre], pv2[kPre], na0 = T(0), na1 = T(0), na2 = T(0);
         // group starting at entry i: size 1 + (following follower bits, at most 2)
@@ -164,14 +194,15 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
                 nsz += (fmask >> (i + 2)) & 1u;
             if (i + nsz > cnt)
                 nsz = cnt - i;
-            nq = __shfl_sync(gm, bs, i, G);
-            nqe = __shfl_sync(gm, be, i, G);
-            na0 = __shfl_sync(gm, av, i, G);
+            const int4 m0 = stage[i], m1 = stage[i + 1], m2 = stage[i + 2];
+            nq = m0.x;
+            nqe = m0.y;
+            na0 = meta_val<T>(m0);
             // twins: offsets of their value rows relative to the first twin's
-            nb1 = __shfl_sync(gm, bs, min(i + 1, G - 1), G) - nq;
-            nb2 = __shfl_sync(gm, bs, min(i + 2, G - 1), G) - nq;
-            na1 = __shfl_sync(gm, av, min(i + 1, G - 1), G);
-            na2 = __shfl_sync(gm, av, min(i + 2, G - 1), G);
+            nb1 = m1.x - nq;
+            nb2 = m2.x - nq;
+            na1 = meta_val<T>(m1);
+            na2 = meta_val<T>(m2);
 #pragma unroll
             for (int t = 0; t < kPre; ++t)
             {
