@@ -334,72 +334,53 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_count(int M, const unsigned
         blockhist[threadIdx.x * nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
-// One block: per bin, exclusive scan of the per-block counts; bin sizes / offsets to scal.
-__global__ void __launch_bounds__(1024) k_bin_offsets(int *__restrict__ blockhist, int nblocks, int nbins,
-                                                      int *__restrict__ size_out, int *__restrict__ off_out)
+// One block, one warp per bin: exclusive scan of that bin's per-block counts (warp shuffle
+// scan, 32 blocks per step), then the bin bases from the 16 totals; sizes / offsets to scal.
+__global__ void __launch_bounds__(32 * MHB_MAX_BINS) k_bin_offsets(int *__restrict__ blockhist, int nblocks,
+                                                                   int nbins, int *__restrict__ size_out,
+                                                                   int *__restrict__ off_out)
 {
-    __shared__ int warp_tot[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0)
-        carry = 0;
-    __syncthreads();
-    int bin_base = 0;
-    for (int b = 0; b < nbins; ++b)
-    {
-        int *h = blockhist + (size_t)b * nblocks;
-        int start = carry; // == bin_base at this point
-        for (int c0 = 0; c0 < nblocks; c0 += 1024)
+    __shared__ int total[MHB_MAX_BINS], base[MHB_MAX_BINS + 1];
+    const int b = threadIdx.x >> 5, lane = lane_id();
+    int *h = blockhist + (size_t)b * nblocks;
+    int carry = 0;
+    if (b < nbins)
+        for (int c0 = 0; c0 < nblocks; c0 += 32)
         {
-            int i = c0 + threadIdx.x;
-            int v = (i < nblocks) ? h[i] : 0;
+            const int i = c0 + lane;
+            const int v = (i < nblocks) ? h[i] : 0;
             int incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
             {
-                int t = __shfl_up_sync(kFull, incl, o);
-                if (lane_id() >= o)
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o)
                     incl += t;
             }
-            if (lane_id() == 31)
-                warp_tot[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            if (threadIdx.x < 32)
-            {
-                int w = warp_tot[threadIdx.x], wi = w;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    int t = __shfl_up_sync(kFull, wi, o);
-                    if (lane_id() >= o)
-                        wi += t;
-                }
-                warp_tot[threadIdx.x] = wi - w;
-            }
-            __syncthreads();
-            int excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
             if (i < nblocks)
-                h[i] = excl;
-            __syncthreads();
-            if (threadIdx.x == 1023)
-                carry = excl + v;
-            __syncthreads();
+                h[i] = carry + incl - v; // exclusive inside the bin; the bin base is added below
+            carry += __shfl_sync(kFull, incl, 31);
         }
-        if (threadIdx.x == 0)
-        {
-            size_out[b] = carry - start;
-            off_out[b] = start;
-        }
-        bin_base = carry;
-    }
+    if (lane == 0)
+        total[b] = (b < nbins) ? carry : 0;
+    __syncthreads();
     if (threadIdx.x == 0)
     {
-        off_out[nbins] = bin_base;
-        for (int b = nbins; b < MHB_MAX_BINS; ++b)
+        int run = 0;
+        for (int q = 0; q < MHB_MAX_BINS; ++q)
         {
-            size_out[b] = 0;
-            off_out[b + 1] = bin_base;
+            base[q] = run;
+            size_out[q] = total[q];
+            off_out[q] = run;
+            run += total[q];
         }
+        base[MHB_MAX_BINS] = run;
+        off_out[MHB_MAX_BINS] = run;
     }
+    __syncthreads();
+    if (b < nbins && base[b] != 0)
+        for (int i = lane; i < nblocks; i += 32)
+            h[i] += base[b];
 }
 
 __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(int M, const unsigned char *__restrict__ binid,

@@ -272,7 +272,7 @@ int run_binning(mhb_context *h, int M, int nbins, int *bins, int size_at, int of
     const unsigned char *binid = h->binid.as<unsigned char>();
     int *bh = h->blockhist.as<int>();
     LAUNCH(h, k_bin_count, nb, kBinThreads, 0, M, binid, bh, nb);
-    LAUNCH(h, k_bin_offsets, 1, 1024, 0, bh, nb, nbins, scal + size_at, scal + off_at);
+    LAUNCH(h, k_bin_offsets, 1, 32 * MHB_MAX_BINS, 0, bh, nb, nbins, scal + size_at, scal + off_at);
     LAUNCH(h, k_bin_scatter, nb, kBinThreads, 0, M, binid, bh, nb, bins);
     return MHB_OK;
 }

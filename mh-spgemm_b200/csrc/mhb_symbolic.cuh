@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kSymThreads)
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     unsigned *bm = sm_u + (size_t)g * wcap;
+    const int gbase = lane_id() & ~(G - 1);
     for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
     {
         const int row = rows[r];
@@ -78,7 +79,8 @@ __global__ void __launch_bounds__(kSymThreads)
             if ((kk & 0x40000000) && (kk & 0x3fffffff) == pk + 1)
                 te = ts;
             prev_k = __shfl_sync(gm, kk & 0x3fffffff, G - 1, G);
-            const int cnt = min(G, e - j0);
+            // visit only the nonzeros that still have tiles to contribute (twins were emptied)
+            unsigned live = (__ballot_sync(gm, te > ts) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
             int pc = -1, nq = 0, nqe = 0;
             unsigned pm = 0u;
             auto issue = [&](int i) {
@@ -91,13 +93,15 @@ __global__ void __launch_bounds__(kSymThreads)
                     pm = __ldg(&tilemask[nq + l]);
                 }
             };
-            issue(0);
-            for (int i = 0; i < cnt; ++i)
+            if (live)
+                issue(__ffs(live) - 1);
+            while (live)
             {
+                live &= live - 1;
                 const int c = pc, q = nq, qe = nqe;
                 const unsigned m = pm;
-                if (i + 1 < cnt)
-                    issue(i + 1);
+                if (live)
+                    issue(__ffs(live) - 1);
                 if (c >= 0)
                     bm[c - tbase] |= m; // tiles of one B row are distinct: no atomic
                 for (int p = q + G + l; p < qe; p += G)
