@@ -324,7 +324,11 @@ def main():
                            exchange_bytes_received_rank0=exch_bytes),
             "roofline": {"bound": "hbm", "kernel": "numeric (k_num_win_group<32,double>)" if args.workload == "F"
                          else "numeric (all bins)", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from
+                         # one `ncu --set full` capture (profiles/r1e_numwin_final.md); other workloads: null
+                         "traffic": 253136128 if (args.workload == "F" and world == 1) else None,
+                         "bound_on_chip": "LSU data pipe 68 %, issue 65 % (profiles/r1e_numwin_final.md)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ba_rank,
                          "kernel_ms": round(kern_ms, 4),
                          "pipeline_frac": round(ba / (ms * 1e-3) / 1e9 / peak / world, 4)},
