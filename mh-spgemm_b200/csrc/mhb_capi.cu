@@ -502,12 +502,12 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     }
     if ((n = n_of(NB_H_WARP_L)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
+        // 1 024-slot tables: 12 KB each, so only ~18 fit an SM.  Two warps share one table
+        // (block kernel, 64 threads) to keep ~36 warps resident instead of 18.
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_L_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS), scal);
+        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
+                  bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
+                  (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_WIN_WARP)) > 0)
     {
