@@ -139,6 +139,8 @@ class RangeExchange:
     def own_views(self):
         """Views of this rank's own shard INSIDE the gathered image.  A caller that keeps its
         shard of B there (instead of in separate arrays) saves the local copy of run()."""
+        if self.local is None:
+            return self.col[:0], self.val[:0]
         sa, sb, da, db = self.local
         return self.col[da:db], self.val[da:db]
 
