@@ -36,7 +36,7 @@ import mh_spgemm_b200  # noqa: E402,F401
 from mh_spgemm_b200 import generators as G  # noqa: E402
 from mh_spgemm_b200.csr import CSR  # noqa: E402
 
-METRIC = "spgemm_gflops"
+METRIC = "SpGEMM GFLOPS (2*intprod/s), C=A*A fp64"
 UNIT = "GFLOPS (2*intprod/s)"
 
 

@@ -64,8 +64,12 @@ class Stats(C.Structure):
 
 def load_library() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not built: run `python mh-spgemm_b200/build.py` "
-                           "(there is no CPU fallback)")
+        try:  # a fresh checkout: compile in-tree with nvcc (seconds); never a CPU substitute
+            from .build import build
+            build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f"{LIB_PATH} not built and nvcc build failed ({e}): run "
+                               "`python mh-spgemm_b200/build.py` (there is no CPU fallback)") from e
     L = C.CDLL(LIB_PATH)
     vp, ip, ll = C.c_void_p, C.c_int, C.c_longlong
     L.mhb_version.restype = C.c_char_p

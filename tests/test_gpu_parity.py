@@ -366,3 +366,33 @@ def test_degenerate_shapes(tool, orc, shape):
     C = tool.spgemm_host(A, B)
     Cp, Cc, Cv = orc.spgemm(A, B)
     assert_matches(orc, C, Cp, Cc, Cv)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_random_shapes(tool, orc, seed):
+    """Seeded fuzz over shapes, densities and row-length skew (rectangular A*B, empty rows and
+    columns, a few very long rows), every accumulator path, both value types."""
+    rng = np.random.default_rng(1000 + seed)
+    M, K, N = (int(rng.integers(1, 400)), int(rng.integers(1, 400)), int(rng.choice([7, 60, 500, 5000, 70000])))
+    def rand(m, n, density, long_rows):
+        nnz = max(1, int(m * n * density))
+        r, c = rng.integers(0, m, nnz), rng.integers(0, n, nnz)
+        for _ in range(long_rows):  # a few rows that touch many columns
+            rr = int(rng.integers(0, m))
+            extra = rng.choice(n, size=min(n, int(rng.integers(1, 600))), replace=False)
+            r, c = np.concatenate([r, np.full(extra.size, rr)]), np.concatenate([c, extra])
+        return CSR.from_coo(m, n, r, c, rng=rng)
+    A = rand(M, K, float(rng.choice([0.002, 0.02, 0.2])), int(rng.integers(0, 3)))
+    B = rand(K, N, float(rng.choice([0.0005, 0.01, 0.1])) if N > 500 else 0.2, int(rng.integers(0, 3)))
+    if seed % 2:
+        A, B = A.astype(np.float32), B.astype(np.float32)
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    for force in ((0, 0), (1, 1), (2, 2)):
+        tool.set_option("force_sym_path", force[0])
+        tool.set_option("force_num_path", force[1])
+        try:
+            C = tool.spgemm_host(A, B)
+        finally:
+            tool.set_option("force_sym_path", 0)
+            tool.set_option("force_num_path", 0)
+        assert_matches(orc, C, Cp, Cc, Cv)
