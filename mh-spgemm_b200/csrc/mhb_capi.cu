@@ -116,7 +116,9 @@ struct mhb_context
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
     int aux_used = 0;
     bool serial = false; // option "serial_bins": one stream, for per-kernel timing
-    DevBuf bsame;
+    DevBuf bsame, asame_buf;
+    const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
+    int row_twins = 1;                   // option "row_twins": fuse twin rows of A in the window kernel
     std::string err;
     // options
     int force_sym = 0, force_num = 0, verbose = 0;
@@ -511,12 +513,23 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     }
     if ((n = n_of(NB_WIN_WARP)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * (NB_WIN_WARP_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
+        if (h->row_twins)
+        {
+            constexpr int WPB = kRowTwinThreads / 32;
+            const size_t smem = (size_t)WPB * 3 * (NB_WIN_WARP_COLS + 34) * sizeof(T) + (size_t)WPB * 34 * 8;
+            LAUNCH_ON(h, st, k_num_win_rowtwins<T>, std::min(cdiv(cdiv(n, 3), WPB), cap_blocks), kRowTwinThreads, smem,
+                      bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_WARP_COLS,
+                      h->bsame.as<unsigned char>(), h->asame);
+        }
+        else
+        {
+            constexpr int G = 32, GPB = kNumGroupThreads / G;
+            auto kern = k_num_win_group<G, T>;
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+                      GPB * (NB_WIN_WARP_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc,
+                      Bv, arow, Cp, Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
+        }
     }
     if ((n = n_of(NB_H_WARP_M)) > 0)
     {
@@ -581,6 +594,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
+    CU(allow_smem(k_num_win_rowtwins<double>, 4 * 3 * (NB_WIN_WARP_COLS + 34) * 8 + 4 * 34 * 8));
+    CU(allow_smem(k_num_win_rowtwins<float>, 4 * 3 * (NB_WIN_WARP_COLS + 34) * 4 + 4 * 34 * 8));
     CU(allow_smem(k_num_win_block<double>, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_num_win_block<float>, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_num_hash_group<32, double>, 8 * NB_H_WARP_L_SLOTS * 12));
@@ -630,6 +645,16 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     rc = build_mask_matrix(h, K, nnzB, Bp, Bc);
     if (rc)
         return rc;
+    // twin rows of A (same column list as the previous row): B's flags when A is B
+    if (Ap == Bp && Ac == Bc)
+        h->asame = h->bsame.as<unsigned char>();
+    else
+    {
+        CU(h->asame_buf.ensure((size_t)M + 1));
+        if (M > 0)
+            LAUNCH(h, k_rows_same_cols, cdiv(M, 256), 256, 0, M, Ap, Ac, h->asame_buf.as<unsigned char>());
+        h->asame = h->asame_buf.as<unsigned char>();
+    }
     CU(cudaEventRecord(h->ev[EV_MASK], h->stream));
 
     // family 2: row metrics + symbolic bins
@@ -895,7 +920,7 @@ extern "C"
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
-                          &h->binid, &h->bsame, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
+                          &h->binid, &h->bsame, &h->asame_buf, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
                           &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
                           &h->sC_col, &h->sC_val})
             b->release();
@@ -944,6 +969,8 @@ extern "C"
             h->force_sym = (int)value;
         else if (k == "force_num_path")
             h->force_num = (int)value;
+        else if (k == "row_twins")
+            h->row_twins = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")
