@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
 SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [

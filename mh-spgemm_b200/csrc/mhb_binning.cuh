@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
 __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restrict__ counts,
                                                       const int4 *__restrict__ arow,
                                                       unsigned char *__restrict__ binid, int *__restrict__ scal,
-                                                      int force_path)
+                                                      int force_path, int force_sym, int compact_ok)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n = 0;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
     {
         n = counts[i];
         int4 info = arow[i];
-        binid[i] = (unsigned char)mhb_classify_num(n, info.x, info.z, info.w, force_path);
+        binid[i] = (unsigned char)mhb_classify_num(n, info.x, info.z, info.w, force_path, info.y, force_sym, compact_ok);
     }
     __shared__ int sh_mx[8];
     n = group_max<32>(n, kFull);

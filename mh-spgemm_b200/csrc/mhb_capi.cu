@@ -116,9 +116,11 @@ struct mhb_context
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
     int aux_used = 0;
     bool serial = false; // option "serial_bins": one stream, for per-kernel timing
-    DevBuf bsame, asame_buf;
+    DevBuf bsame, asame_buf, bm_store, bm_slot;
+    bool have_bm_store = false;          // symbolic kept the bitmaps of its SB_BM_G8 rows
+    int compact_rows = 1;                // option "compact_rows": use NB_WIN_COMPACT
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
-    int row_twins = 1;                   // option "row_twins": fuse twin rows of A in the window kernel
+    int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
     std::string err;
     // options
     int force_sym = 0, force_num = 0, verbose = 0;
@@ -368,6 +370,7 @@ int launch_symbolic_bins(mhb_context *h)
     const int cap_blocks = h->num_sms * 16;
     int n;
     cudaStream_t st;
+    h->have_bm_store = false;
     int frc = fork_bins(h);
     if (frc)
         return frc;
@@ -419,7 +422,7 @@ int launch_symbolic_bins(mhb_context *h)
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>());
+               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>(), (unsigned *)nullptr, (int *)nullptr);
     }
     if ((n = n_of(SB_H_G8)) > 0)
     {
@@ -432,10 +435,19 @@ int launch_symbolic_bins(mhb_context *h)
     if ((n = n_of(SB_BM_G8)) > 0)
     {
         constexpr int G = 8, GPB = kSymThreads / G;
+        // keep the bitmaps of these rows for the numeric pass (NB_WIN_COMPACT) when that is cheap
+        const size_t store_bytes = (size_t)n * SB_BM_STORE_WORDS * 4;
+        h->have_bm_store = h->compact_rows && store_bytes <= ((size_t)1 << 31);
+        if (h->have_bm_store)
+        {
+            CU(h->bm_store.ensure(store_bytes));
+            CU(h->bm_slot.ensure(((size_t)h->M + 1) * 4));
+        }
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_G8_WORDS, h->bsame.as<unsigned char>());
+               SB_BM_G8_WORDS, h->bsame.as<unsigned char>(), h->have_bm_store ? h->bm_store.as<unsigned>() : nullptr,
+               h->have_bm_store ? h->bm_slot.as<int>() : nullptr);
     }
     if ((n = n_of(SB_TINY)) > 0)
     {
@@ -510,6 +522,16 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
                   bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
                   (unsigned char *)nullptr, 0LL, scal);
+    }
+    if ((n = n_of(NB_WIN_COMPACT)) > 0)
+    {
+        constexpr int WPB = kRowTwinThreads / 32;
+        const size_t smem = (size_t)WPB * 3 * (NB_WIN_COMPACT_MAXN + 34) * sizeof(T) +
+                            (size_t)WPB * (SB_BM_STORE_WORDS + 2 + 34) * 8;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_num_compact_rowtwins<T>, std::min(cdiv(cdiv(n, 3), WPB), cap_blocks), kRowTwinThreads, smem,
+                  bins + off[NB_WIN_COMPACT], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_COMPACT_MAXN,
+                  h->bsame.as<unsigned char>(), h->asame, h->bm_store.as<unsigned>(), h->bm_slot.as<int>());
     }
     if ((n = n_of(NB_WIN_WARP)) > 0)
     {
@@ -594,6 +616,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
+    CU(allow_smem(k_num_compact_rowtwins<double>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 8 + 4 * 100 * 8));
+    CU(allow_smem(k_num_compact_rowtwins<float>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 4 + 4 * 100 * 8));
     CU(allow_smem(k_num_win_rowtwins<double>, 4 * 3 * (NB_WIN_WARP_COLS + 34) * 8 + 4 * 34 * 8));
     CU(allow_smem(k_num_win_rowtwins<float>, 4 * 3 * (NB_WIN_WARP_COLS + 34) * 4 + 4 * 34 * 8));
     CU(allow_smem(k_num_win_block<double>, MHB_SMEM_MAX - 256));
@@ -645,16 +669,6 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     rc = build_mask_matrix(h, K, nnzB, Bp, Bc);
     if (rc)
         return rc;
-    // twin rows of A (same column list as the previous row): B's flags when A is B
-    if (Ap == Bp && Ac == Bc)
-        h->asame = h->bsame.as<unsigned char>();
-    else
-    {
-        CU(h->asame_buf.ensure((size_t)M + 1));
-        if (M > 0)
-            LAUNCH(h, k_rows_same_cols, cdiv(M, 256), 256, 0, M, Ap, Ac, h->asame_buf.as<unsigned char>());
-        h->asame = h->asame_buf.as<unsigned char>();
-    }
     CU(cudaEventRecord(h->ev[EV_MASK], h->stream));
 
     // family 2: row metrics + symbolic bins
@@ -692,7 +706,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     // family 2 again: numeric bins from the exact row sizes, then the row-offset scan
     if (M > 0)
         LAUNCH(h, k_classify_num, cdiv(M, 256), 256, 0, M, Cp, h->arow.as<int4>(), h->binid.as<unsigned char>(),
-               scal, h->force_num);
+               scal, h->force_num, h->force_sym, h->have_bm_store ? 1 : 0);
     rc = run_binning(h, M, NB_COUNT, h->bins_num.as<int>(), SC_NUM_SIZE, SC_NUM_OFF);
     if (rc)
         return rc;
@@ -724,6 +738,20 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     if (h->nnzC > h->nnz_limit)
         return fail(h, MHB_ERR_OVERFLOW,
                     "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the int32 CSR contract; shard the rows of A");
+    // twin rows of A (same column list as the previous row), needed only by the row-twin numeric
+    // kernels: B's flags when A is B, else compared now -- off the symbolic critical path
+    if (Ap == Bp && Ac == Bc)
+        h->asame = h->bsame.as<unsigned char>();
+    else
+    {
+        CU(h->asame_buf.ensure((size_t)M + 1));
+        const bool needed = (h->num_off[NB_WIN_COMPACT + 1] > h->num_off[NB_WIN_COMPACT]) ||
+                            (h->row_twins && h->num_off[NB_WIN_WARP + 1] > h->num_off[NB_WIN_WARP]);
+        if (M > 0 && needed)
+            LAUNCH(h, k_rows_same_cols, cdiv((long long)M * 8, 256), 256, 0, M, Ap, Ac,
+                   h->asame_buf.as<unsigned char>());
+        h->asame = h->asame_buf.as<unsigned char>();
+    }
     h->have_pattern = true;
     if (h->verbose)
         std::printf("C.nnz = %lld\n", h->nnzC); // the reference's print (src/main.cu:58), opt-in
@@ -920,7 +948,7 @@ extern "C"
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
-                          &h->binid, &h->bsame, &h->asame_buf, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
+                          &h->binid, &h->bsame, &h->asame_buf, &h->bm_store, &h->bm_slot, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
                           &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
                           &h->sC_col, &h->sC_val})
             b->release();
@@ -969,6 +997,8 @@ extern "C"
             h->force_sym = (int)value;
         else if (k == "force_num_path")
             h->force_num = (int)value;
+        else if (k == "compact_rows")
+            h->compact_rows = (int)value;
         else if (k == "row_twins")
             h->row_twins = (int)value;
         else if (k == "nnz_limit")

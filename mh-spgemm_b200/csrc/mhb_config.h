@@ -62,6 +62,8 @@ enum MhbNumBin
     NB_TINY,        // one thread per row, n <= 16 and <= 128 products
     NB_H_WARP_XS,   // hash, warp/row,    n <= 80  (128 slots)
     NB_H_WARP_M,    // hash, warp/row,    n <= 320 (512 slots)
+    NB_WIN_COMPACT, // window rows with a stored symbolic bitmap, n <= 448: rank-mapped accumulators,
+                    // up to three twin rows of A per warp
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -82,6 +84,8 @@ enum MhbNumBin
 #define NB_H_BLOCK_S_MAX 2560
 #define NB_H_BLOCK_L_SLOTS 16384
 #define NB_H_BLOCK_L_MAX 10240
+#define NB_WIN_COMPACT_MAXN 448
+#define SB_BM_STORE_WORDS 64 // stride of a stored symbolic bitmap (the SB_BM_G8 bin)
 #define NB_TINY_MAX 16
 #define NB_TINY_PRODUCTS 128
 #define NB_WINDOW_WORK_FACTOR 32 // window when W <= 32 * n (or W <= 64)
@@ -126,7 +130,8 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
 }
 
 // Row metrics -> numeric bin.  n = nnz of the C row.
-MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force)
+MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf = 0, int force_sym = 0,
+                            int compact_ok = 0)
 {
     if (n <= 0)
         return NB_EMPTY;
@@ -144,7 +149,10 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force)
         if (w <= NB_WIN_G8_COLS)
             return NB_WIN_G8;
         if (w <= NB_WIN_WARP_COLS)
-            return NB_WIN_WARP;
+            return (compact_ok && n <= NB_WIN_COMPACT_MAXN &&
+                    mhb_classify_sym(ip, tf, cmin, cmax, force_sym) == SB_BM_G8)
+                       ? NB_WIN_COMPACT
+                       : NB_WIN_WARP;
         return w <= NB_WIN_BLOCK_S_COLS ? NB_WIN_BLOCK_S : NB_WIN_BLOCK_L;
     }
     if (n <= NB_H_G8_MAX)

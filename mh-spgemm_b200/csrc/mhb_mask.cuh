@@ -169,30 +169,34 @@ __global__ void __launch_bounds__(256) k_mask_same(int K, const int4 *__restrict
 
 // same[r] = 1 when row r of a CSR matrix has exactly the column list of row r-1 (used for the
 // rows of A when A is not the same array as B; B's flags come from its tile lists above).
+// 8 lanes per row compare the two column lists side by side (coalesced), group vote.
 __global__ void __launch_bounds__(256) k_rows_same_cols(int M, const int *__restrict__ ptr,
                                                         const int *__restrict__ col,
                                                         unsigned char *__restrict__ same)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= M)
-        return;
-    unsigned char eq = 0;
-    if (r > 0)
+    constexpr int G = 8;
+    const int l = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool valid = gid < M && gid > 0;
+    const int r = valid ? (int)gid : 1;
+    bool eq = false;
+    if (valid)
     {
         const int a0 = ptr[r - 1], b0 = ptr[r], b1 = ptr[r + 1];
         const int len = b1 - b0;
-        if (len > 0 && len == b0 - a0 && col[a0] == col[b0] && col[b0 - 1] == col[b1 - 1])
-        {
-            eq = 1;
-            for (int t = 1; t < len - 1; ++t)
+        eq = len > 0 && len == b0 - a0;
+        if (eq)
+            for (int t = l; t < len; t += G)
                 if (col[a0 + t] != col[b0 + t])
                 {
-                    eq = 0;
+                    eq = false;
                     break;
                 }
-        }
     }
-    same[r] = eq;
+    const bool all_eq = __all_sync(gm, eq);
+    if (l == 0 && gid < M)
+        same[gid] = (valid && all_eq) ? 1 : 0;
 }
 
 } // namespace mhb

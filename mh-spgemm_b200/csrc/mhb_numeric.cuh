@@ -290,6 +290,237 @@ __global__ void __launch_bounds__(kRowTwinThreads)
 }
 
 // =========================================================================================
+// Rank-mapped ("compact") window, one warp per group of up to three twin rows of A.
+// The symbolic pass kept the occupancy bitmap of these rows (bm_store, <= 64 words).  A warp
+// scan of the word popcounts gives, for every 32-column word, the number of C entries in
+// front of it; a product with column c then accumulates into
+//     acc[ prefix[word(c)] + popc(mask[word(c)] & bits_below(c)) ]        (one LDS.64 lookup)
+// i.e. directly into its final CSR position.  Against the dense window this needs no
+// "unset" marker (init 0, always add), no compaction sweep, and 8 bytes per ENTRY instead of
+// per COLUMN of the span -- which is what makes three accumulator sets per warp affordable
+// (the dense-window row-twin kernel above drops to 8 warps/SM and loses).  The lookup is
+// shared by the three twin rows: v_r = sum_j a[r][j] * b_j lands in acc_r[rank].
+// smem per warp: lut[66] (mask, prefix) | 3 x acc[ncap] | stage_be[G+2] | stage_a[3][G+2]
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kRowTwinThreads)
+    k_num_compact_rowtwins(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                           const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
+                           const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
+                           const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int ncap,
+                           const unsigned char *__restrict__ bsame, const unsigned char *__restrict__ asame,
+                           const unsigned *__restrict__ bm_store, const int *__restrict__ bm_slot)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    constexpr int G = 32, WPB = kRowTwinThreads / 32, SG = G + 2, LUT = SB_BM_STORE_WORDS + 2;
+    const int warp = threadIdx.x >> 5, l = lane_id();
+    // layout (per block): acc[WPB][3][ncap] T | stage_a[WPB][3][SG] T | lut[WPB][LUT] uint2 | stage_be[WPB][SG] int2
+    T *acc0 = reinterpret_cast<T *>(sm_raw) + (size_t)warp * 3 * ncap;
+    T *stage_a = reinterpret_cast<T *>(sm_raw) + (size_t)WPB * 3 * ncap + (size_t)warp * 3 * SG;
+    uint2 *lut = reinterpret_cast<uint2 *>(reinterpret_cast<T *>(sm_raw) + (size_t)WPB * 3 * (ncap + SG)) +
+                 (size_t)warp * LUT;
+    int2 *stage_be = reinterpret_cast<int2 *>(reinterpret_cast<uint2 *>(
+                         reinterpret_cast<T *>(sm_raw) + (size_t)WPB * 3 * (ncap + SG)) + (size_t)WPB * LUT) +
+                     (size_t)warp * SG;
+    for (int chunk = blockIdx.x * WPB + warp; chunk * 3 < nrows; chunk += gridDim.x * WPB)
+    {
+        const int base = chunk * 3, cnt3 = min(3, nrows - base);
+        int j = 0;
+        while (j < cnt3)
+        {
+            const int row = __ldg(&rows[base + j]);
+            int R = 1;
+            if (j + 1 < cnt3 && __ldg(&rows[base + j + 1]) == row + 1 && __ldg(&asame[row + 1]))
+            {
+                R = 2;
+                if (j + 2 < cnt3 && __ldg(&rows[base + j + 2]) == row + 2 && __ldg(&asame[row + 2]))
+                    R = 3;
+            }
+            j += R;
+            const int4 info = __ldg(&arow[row]);
+            const int tbase = info.z >> MHB_TILE_SHIFT;
+            const int wt = (info.w >> MHB_TILE_SHIFT) - tbase + 1; // <= 64 (SB_BM_G8 rows)
+            // lookup table: (mask, entries in front of the word), two words per lane
+            const unsigned *bmrow = bm_store + (size_t)__ldg(&bm_slot[row]) * SB_BM_STORE_WORDS;
+            const unsigned m0 = (l < wt) ? __ldg(&bmrow[l]) : 0u;
+            const unsigned m1 = (l + 32 < wt) ? __ldg(&bmrow[l + 32]) : 0u;
+            int c0 = __popc(m0), c1 = __popc(m1);
+            int i0 = c0, i1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t0 = __shfl_up_sync(kFull, i0, o), t1 = __shfl_up_sync(kFull, i1, o);
+                if (l >= o)
+                    i0 += t0, i1 += t1;
+            }
+            const int n0 = __shfl_sync(kFull, i0, 31);
+            const int n = n0 + __shfl_sync(kFull, i1, 31); // nnz of the row(s)
+            lut[l] = make_uint2(m0, (unsigned)(i0 - c0));
+            lut[l + 32] = make_uint2(m1, (unsigned)(n0 + i1 - c1));
+            for (int r = 0; r < R; ++r)
+                for (int i = l; i < n; i += G)
+                    acc0[r * ncap + i] = T(0);
+            if (l < 2)
+            {
+                stage_be[G + l] = make_int2(0, 0);
+                stage_a[0 * SG + G + l] = stage_a[1 * SG + G + l] = stage_a[2 * SG + G + l] = T(0);
+            }
+            __syncwarp();
+            const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+            const int d1 = (R > 1) ? __ldg(&Ap[row + 1]) - s : 0, d2 = (R > 2) ? __ldg(&Ap[row + 2]) - s : 0;
+            int bs, be, kk, nbs, nbe, nkk;
+            T av0, av1 = T(0), av2 = T(0), nav0, nav1 = T(0), nav2 = T(0);
+            auto meta = [&](int jj, int &ms, int &me, int &mk, T &a0, T &a1, T &a2) {
+                ms = 0, me = 0, mk = -2, a0 = T(0), a1 = T(0), a2 = T(0);
+                if (jj < e)
+                {
+                    mk = __ldg(&Ac[jj]);
+                    a0 = __ldg(&Av[jj]);
+                    if (R > 1)
+                        a1 = __ldg(&Av[jj + d1]);
+                    if (R > 2)
+                        a2 = __ldg(&Av[jj + d2]);
+                    ms = __ldg(&Bp[mk]);
+                    me = __ldg(&Bp[mk + 1]);
+                    if (__ldg(&bsame[mk]))
+                        mk |= 0x40000000;
+                }
+            };
+            meta(s + l, bs, be, kk, av0, av1, av2);
+            for (int j0 = s; j0 < e; j0 += G)
+            {
+                meta(j0 + G + l, nbs, nbe, nkk, nav0, nav1, nav2);
+                const int cnt = min(G, e - j0);
+                stage_be[l] = make_int2(bs, be);
+                stage_a[0 * SG + l] = av0;
+                stage_a[1 * SG + l] = av1;
+                stage_a[2 * SG + l] = av2;
+                const int kprev = __shfl_up_sync(kFull, kk & 0x3fffffff, 1);
+                const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
+                const unsigned fmask = __ballot_sync(kFull, fol);
+                __syncwarp();
+                int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0, ni = 0;
+                T pv0[kPre], pv1[kPre], pv2[kPre];
+                auto issue = [&](int i) {
+                    ni = i;
+                    nsz = 1 + ((fmask >> (i + 1)) & 1u);
+                    if (nsz == 2)
+                        nsz += (fmask >> (i + 2)) & 1u;
+                    if (i + nsz > cnt)
+                        nsz = cnt - i;
+                    const int2 e0 = stage_be[i], e1 = stage_be[i + 1], e2 = stage_be[i + 2];
+                    nq = e0.x;
+                    nqe = e0.y;
+                    nb1 = e1.x - nq;
+                    nb2 = e2.x - nq;
+#pragma unroll
+                    for (int t = 0; t < kPre; ++t)
+                    {
+                        const int p = nq + t * G + l;
+                        pc[t] = -1;
+                        if (p < nqe)
+                        {
+                            pc[t] = __ldg(&Bc[p]);
+                            pv0[t] = __ldg(&Bv[p]);
+                            if (nsz > 1)
+                                pv1[t] = __ldg(&Bv[p + nb1]);
+                            if (nsz > 2)
+                                pv2[t] = __ldg(&Bv[p + nb2]);
+                        }
+                    }
+                };
+                auto rank_of = [&](int c) {
+                    const uint2 w = lut[(c >> MHB_TILE_SHIFT) - tbase];
+                    return (int)w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
+                };
+                issue(0);
+                for (int i = 0; i < cnt;)
+                {
+                    int rk[kPre];
+                    T b0[kPre], b1[kPre], b2[kPre];
+                    bool act[kPre];
+                    const int q = nq, qe = nqe, sz = nsz, o1 = nb1, o2 = nb2, ci = ni;
+#pragma unroll
+                    for (int t = 0; t < kPre; ++t)
+                    {
+                        act[t] = pc[t] >= 0;
+                        rk[t] = act[t] ? rank_of(pc[t]) : 0; // idle lanes point at entry 0 and store nothing
+                        b0[t] = pv0[t], b1[t] = pv1[t], b2[t] = pv2[t];
+                    }
+                    i += sz;
+                    if (i < cnt)
+                        issue(i);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                    {
+                        if (r >= R)
+                            break;
+                        const T a0 = stage_a[r * SG + ci];
+                        const T a1 = (sz > 1) ? stage_a[r * SG + ci + 1] : T(0);
+                        const T a2 = (sz > 2) ? stage_a[r * SG + ci + 2] : T(0);
+                        T *acc = acc0 + r * ncap;
+#pragma unroll
+                        for (int t = 0; t < kPre; ++t)
+                        {
+                            T v = a0 * b0[t];
+                            if (sz > 1)
+                                v = fma(a1, b1[t], v);
+                            if (sz > 2)
+                                v = fma(a2, b2[t], v);
+                            const T o = acc[rk[t]];
+                            if (act[t])
+                                acc[rk[t]] = o + v; // columns of one step are distinct: no atomic
+                        }
+                        for (int p = q + kPre * G + l; p < qe; p += G) // B rows longer than kPre*G
+                        {
+                            T v = a0 * __ldg(&Bv[p]);
+                            if (sz > 1)
+                                v = fma(a1, __ldg(&Bv[p + o1]), v);
+                            if (sz > 2)
+                                v = fma(a2, __ldg(&Bv[p + o2]), v);
+                            const int k = rank_of(__ldg(&Bc[p]));
+                            acc[k] += v;
+                        }
+                    }
+                    __syncwarp();
+                }
+                bs = nbs, be = nbe, kk = nkk, av0 = nav0, av1 = nav1, av2 = nav2;
+            }
+            // values are already in CSR order: coalesced copies; columns come from the bitmap
+            const int out0 = __ldg(&Cp[row]);
+            const int q1 = (R > 1) ? __ldg(&Cp[row + 1]) : 0, q2 = (R > 2) ? __ldg(&Cp[row + 2]) : 0;
+            for (int i = l; i < n; i += G)
+            {
+                Cv[out0 + i] = acc0[i];
+                if (R > 1)
+                    Cv[q1 + i] = acc0[ncap + i];
+                if (R > 2)
+                    Cv[q2 + i] = acc0[2 * ncap + i];
+            }
+            for (int w = l; w < wt; w += G)
+            {
+                const uint2 e = lut[w];
+                unsigned m = e.x;
+                int k = (int)e.y;
+                const int cbase = ((tbase + w) << MHB_TILE_SHIFT);
+                while (m)
+                {
+                    const int c = cbase + __ffs(m) - 1;
+                    m &= m - 1;
+                    Cc[out0 + k] = c;
+                    if (R > 1)
+                        Cc[q1 + k] = c;
+                    if (R > 2)
+                        Cc[q2 + k] = c;
+                    ++k;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// =========================================================================================
 // Block-wide helpers
 // =========================================================================================
 // exclusive scan of one int per thread across the block; returns exclusive prefix, *total

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(kSymThreads)
                        const int *__restrict__ Ac, const int *__restrict__ tileptr,
                        const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                        const int4 *__restrict__ arow, int *__restrict__ counts, int wcap,
-                       const unsigned char *__restrict__ same)
+                       const unsigned char *__restrict__ same, unsigned *__restrict__ bm_store,
+                       int *__restrict__ bm_slot)
 {
     extern __shared__ unsigned sm_u[];
     constexpr int GPB = kSymThreads / G;
@@ -112,10 +113,19 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         int c = 0;
         for (int w = l; w < wt; w += G)
-            c += __popc(bm[w]);
+        {
+            const unsigned m = bm[w];
+            c += __popc(m);
+            if (bm_store) // keep the row's pattern for the numeric pass (NB_WIN_COMPACT)
+                bm_store[(size_t)r * SB_BM_STORE_WORDS + w] = m;
+        }
         c = group_sum<G>(c, gm);
         if (l == 0)
+        {
             counts[row] = c;
+            if (bm_store)
+                bm_slot[row] = r;
+        }
         __syncwarp(gm);
     }
 }
