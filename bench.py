@@ -369,13 +369,14 @@ def main():
                                         ("B row-sharded like A, referenced row range gathered by NCCL send/recv "
                                          "each step" if use_range else "B NCCL-broadcast from rank 0 each step")),
                            exchange_bytes_received_rank0=exch_bytes),
-            "roofline": {"bound": "hbm", "kernel": "numeric (k_num_win_group<32,double>)" if args.workload == "F"
+            "roofline": {"bound": "hbm", "kernel": "numeric (k_num_compact_rowtwins<double>)" if args.workload == "F"
                          else "numeric (all bins)", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from
-                         # one `ncu --set full` capture (profiles/r1e_numwin_final.md); other workloads: null
-                         "traffic": 253136128 if (args.workload == "F" and world == 1) else None,
-                         "bound_on_chip": "LSU data pipe 68 %, issue 65 % (profiles/r1e_numwin_final.md)",
+                         # one `ncu --set full` capture (profiles/r1f_numcompact_final.md); other workloads: null
+                         "traffic": 243588608 if (args.workload == "F" and world == 1) else None,
+                         "bound_on_chip": "latency at 13 warps/SM; LSU data pipe 52 %, issue 50 % "
+                                          "(profiles/r1f_numcompact_final.md)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ba_rank,
                          "kernel_ms": round(kern_ms, 4),
                          "pipeline_frac": round(ba / (ms * 1e-3) / 1e9 / peak / world, 4)},
