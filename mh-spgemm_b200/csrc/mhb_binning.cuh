@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
 }
 
 // Numeric bin id from the exact nnz of every C row (counts, before the scan).
-__global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restrict__ counts,
+__global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restrict__ Ap,
+                                                      const int *__restrict__ counts,
                                                       const int4 *__restrict__ arow,
                                                       unsigned char *__restrict__ binid, int *__restrict__ scal,
                                                       int force_path, int force_sym, int compact_ok)
@@ -294,7 +295,9 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
     {
         n = counts[i];
         int4 info = arow[i];
-        binid[i] = (unsigned char)mhb_classify_num(n, info.x, info.z, info.w, force_path, info.y, force_sym, compact_ok);
+        const int na = Ap[i + 1] - Ap[i];
+        binid[i] = (unsigned char)mhb_classify_num(n, info.x, info.z, info.w, force_path, info.y, force_sym, compact_ok,
+                                                   na > 0 ? info.x / na : 0);
     }
     __shared__ int sh_mx[8];
     n = group_max<32>(n, kFull);

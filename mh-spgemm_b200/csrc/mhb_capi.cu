@@ -705,7 +705,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
 
     // family 2 again: numeric bins from the exact row sizes, then the row-offset scan
     if (M > 0)
-        LAUNCH(h, k_classify_num, cdiv(M, 256), 256, 0, M, Cp, h->arow.as<int4>(), h->binid.as<unsigned char>(),
+        LAUNCH(h, k_classify_num, cdiv(M, 256), 256, 0, M, Ap, Cp, h->arow.as<int4>(), h->binid.as<unsigned char>(),
                scal, h->force_num, h->force_sym, h->have_bm_store ? 1 : 0);
     rc = run_binning(h, M, NB_COUNT, h->bins_num.as<int>(), SC_NUM_SIZE, SC_NUM_OFF);
     if (rc)

@@ -130,8 +130,9 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
 }
 
 // Row metrics -> numeric bin.  n = nnz of the C row.
+// avg_b = intermediate products / nonzeros of the A row = mean length of the B rows it selects
 MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf = 0, int force_sym = 0,
-                            int compact_ok = 0)
+                            int compact_ok = 0, int avg_b = 0)
 {
     if (n <= 0)
         return NB_EMPTY;
@@ -146,7 +147,7 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf
         dense = false;
     if (dense)
     {
-        if (w <= NB_WIN_G8_COLS)
+        if (w <= NB_WIN_G8_COLS && avg_b <= 16) // short B rows: 8 lanes per row are enough
             return NB_WIN_G8;
         if (w <= NB_WIN_WARP_COLS)
             return (compact_ok && n <= NB_WIN_COMPACT_MAXN &&
