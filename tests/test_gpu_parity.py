@@ -396,3 +396,30 @@ def test_fuzz_random_shapes(tool, orc, seed):
             tool.set_option("force_sym_path", 0)
             tool.set_option("force_num_path", 0)
         assert_matches(orc, C, Cp, Cc, Cv)
+
+
+@pytest.mark.parametrize("opts", [dict(compact_rows=0), dict(compact_rows=0, row_twins=1), dict(compact_rows=1)])
+@pytest.mark.parametrize("alias", [True, False])
+def test_window_kernel_variants_on_twin_rows(orc, opts, alias):
+    """Multi-dof FEM input (twin rows in A and B): the dense-window kernel with B-twin folding,
+    the dense A-row-twin kernel and the rank-mapped compact kernel must agree with the oracle,
+    with B aliasing A (twin flags shared) and with B a separate copy (flags recomputed)."""
+    t = api.Tool(0)
+    for k, v in opts.items():
+        t.set_option(k, v)
+    A = G.fem3d(5, 4, 14, 3, seed=31)
+    B = A if alias else CSR(A.M, A.N, A.ptr.copy(), A.col.copy(), A.val.copy() * 0.5 + 0.25)
+    C = t.spgemm_host(A, B)
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    assert_matches(orc, C, Cp, Cc, Cv)
+    nb = t.stats["num_bins"]
+    assert (nb["WIN_COMPACT"] > 0) == bool(opts.get("compact_rows", 1))
+    # rows whose twins are broken up (every third row emptied) still come out right
+    keep = np.ones(A.M, bool)
+    keep[1::3] = False
+    rows = np.repeat(np.arange(A.M), np.diff(A.ptr))
+    A2 = CSR.from_coo(A.M, A.N, rows[keep[rows]], A.col[keep[rows]], A.val[keep[rows]])
+    C2 = t.spgemm_host(A2, B)
+    Cp2, Cc2, Cv2 = orc.spgemm(A2, B)
+    assert_matches(orc, C2, Cp2, Cc2, Cv2)
+    t.release()
