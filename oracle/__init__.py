@@ -158,11 +158,11 @@ class Reference:
         L.mhref_spgemm.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p,
                                    C.c_int, C.c_int, C.c_int, _i32p, C.POINTER(ip), C.POINTER(dp),
                                    C.POINTER(C.c_int), dp, dp, _f64p,
-                                   C.c_void_p, C.POINTER(ip), C.POINTER(up)]
+                                   C.c_void_p, C.POINTER(ip), C.POINTER(up), dp]
         L.mhref_cusparse.restype = C.c_int
         L.mhref_cusparse.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p,
                                      C.c_int, C.c_int, _i32p, C.POINTER(ip), C.POINTER(dp),
-                                     C.POINTER(C.c_int), dp]
+                                     C.POINTER(C.c_int), dp, dp]
         self.L = L
 
     @staticmethod
@@ -184,7 +184,7 @@ class Reference:
         cc = C.POINTER(C.c_int)()
         cv = C.POINTER(C.c_double)()
         nnz = C.c_int(0)
-        msd, mse = C.c_double(0), C.c_double(0)
+        msd, mse, msmin = C.c_double(0), C.c_double(0), C.c_double(0)
         stage = np.zeros(7, np.float64)
         tileptr = np.zeros(B.M + 1, np.int32)
         tc = C.POINTER(C.c_int)()
@@ -193,12 +193,13 @@ class Reference:
             A.M, A.N, B.N, A.ptr, A.col, A.val, B.ptr, B.col, B.val, reps, warmup, e2e_reps, Cp,
             C.byref(cc), C.byref(cv), C.byref(nnz), C.byref(msd), C.byref(mse), stage,
             tileptr.ctypes.data if want_mask else None,
-            C.byref(tc) if want_mask else None, C.byref(tm) if want_mask else None)
+            C.byref(tc) if want_mask else None, C.byref(tm) if want_mask else None, C.byref(msmin))
         if rc != 0:
             raise RuntimeError("reference MH_spgemm failed")
         n = int(nnz.value)
         out = dict(ptr=Cp, col=self._take(cc, n, np.int32), val=self._take(cv, n, np.float64), nnz=n,
-                   ms_device=float(msd.value), ms_e2e=float(mse.value), stage_ms=stage)
+                   ms_device=float(msd.value), ms_e2e=float(mse.value), stage_ms=stage,
+                   ms_device_min=float(msmin.value))
         if want_mask:
             nt = int(tileptr[-1])
             out["mask"] = (tileptr, self._take(tc, nt, np.int32), self._take(tm, nt, np.uint32))
@@ -209,11 +210,11 @@ class Reference:
         cc = C.POINTER(C.c_int)()
         cv = C.POINTER(C.c_double)()
         nnz = C.c_int(0)
-        msd = C.c_double(0)
+        msd, msmin = C.c_double(0), C.c_double(0)
         rc = self.L.mhref_cusparse(A.M, A.N, B.N, A.ptr, A.col, A.val, B.ptr, B.col, B.val, reps, warmup,
-                                   Cp, C.byref(cc), C.byref(cv), C.byref(nnz), C.byref(msd))
+                                   Cp, C.byref(cc), C.byref(cv), C.byref(nnz), C.byref(msd), C.byref(msmin))
         if rc != 0:
             raise RuntimeError("cuSPARSE SpGEMM failed")
         n = int(nnz.value)
         return dict(ptr=Cp, col=self._take(cc, n, np.int32), val=self._take(cv, n, np.float64), nnz=n,
-                    ms_device=float(msd.value))
+                    ms_device=float(msd.value), ms_device_min=float(msmin.value))
