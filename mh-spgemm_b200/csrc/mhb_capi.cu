@@ -601,7 +601,8 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     if ((n = n_of(NB_TINY)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads, 0,
+        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
+                  NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4),
                   bins + off[NB_TINY], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
     }
     return join_bins(h);
@@ -616,6 +617,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
+    CU(allow_smem(k_num_tiny<double>, NB_TINY_MAX * kTinyRowThreads * 12));
+    CU(allow_smem(k_num_tiny<float>, NB_TINY_MAX * kTinyRowThreads * 8));
     CU(allow_smem(k_num_compact_rowtwins<double>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 8 + 4 * 100 * 8));
     CU(allow_smem(k_num_compact_rowtwins<float>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 4 + 4 * 100 * 8));
     CU(allow_smem(k_num_win_rowtwins<double>, 4 * 3 * (NB_WIN_WARP_COLS + 34) * 8 + 4 * 34 * 8));

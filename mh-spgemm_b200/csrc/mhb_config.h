@@ -59,7 +59,7 @@ enum MhbNumBin
     NB_H_BLOCK_S,   // hash, block/row,   n <= 2560 (4096 slots)
     NB_H_BLOCK_L,   // hash, block/row,   n <= 10240 (16384 slots)
     NB_H_GLOBAL,    // hash in global memory
-    NB_TINY,        // one thread per row, n <= 16 and <= 128 products
+    NB_TINY,        // one thread per row, n <= 24 and <= 128 products
     NB_H_WARP_XS,   // hash, warp/row,    n <= 80  (128 slots)
     NB_H_WARP_M,    // hash, warp/row,    n <= 320 (512 slots)
     NB_WIN_COMPACT, // window rows with a stored symbolic bitmap, n <= 448: rank-mapped accumulators,
@@ -86,7 +86,7 @@ enum MhbNumBin
 #define NB_H_BLOCK_L_MAX 10240
 #define NB_WIN_COMPACT_MAXN 448
 #define SB_BM_STORE_WORDS 64 // stride of a stored symbolic bitmap (the SB_BM_G8 bin)
-#define NB_TINY_MAX 16
+#define NB_TINY_MAX 24
 #define NB_TINY_PRODUCTS 128
 #define NB_WINDOW_WORK_FACTOR 32 // window when W <= 32 * n (or W <= 64)
 

@@ -1040,9 +1040,9 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
 }
 
 // ---- tiny rows: one thread per row ------------------------------------------------------
-// n <= NB_TINY_MAX entries and <= NB_TINY_PRODUCTS products.  The thread appends (column,
+// n <= NB_TINY_MAX (24) entries and <= NB_TINY_PRODUCTS products.  The thread appends (column,
 // value) pairs to its own shared-memory column (bank = thread, conflict-free), merging
-// repeats by a linear scan, insertion-sorts the <= 16 pairs and writes them out.  ~10x fewer
+// repeats by a linear scan, insertion-sorts the <= 24 pairs and writes them out.  ~10x fewer
 // warp instructions per row than the 8-lane hash kernel (profiles/r1c_tiny_rows.md).
 template <typename T>
 __global__ void __launch_bounds__(kTinyRowThreads)
@@ -1050,8 +1050,9 @@ __global__ void __launch_bounds__(kTinyRowThreads)
                const T *__restrict__ Av, const int *__restrict__ Bp, const int *__restrict__ Bc,
                const T *__restrict__ Bv, const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv)
 {
-    __shared__ int keys[NB_TINY_MAX * kTinyRowThreads];
-    __shared__ T vals[NB_TINY_MAX * kTinyRowThreads];
+    extern __shared__ __align__(16) unsigned char sm_raw[]; // vals[NB_TINY_MAX][threads] | keys[NB_TINY_MAX][threads]
+    T *vals = reinterpret_cast<T *>(sm_raw);
+    int *keys = reinterpret_cast<int *>(vals + NB_TINY_MAX * kTinyRowThreads);
     const int t = threadIdx.x;
     for (int r = blockIdx.x * kTinyRowThreads + t; r < nrows; r += gridDim.x * kTinyRowThreads)
     {
