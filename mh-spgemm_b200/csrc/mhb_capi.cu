@@ -119,6 +119,7 @@ struct mhb_context
     DevBuf bsame, asame_buf, bm_store, bm_slot;
     bool have_bm_store = false;          // symbolic kept the bitmaps of its SB_BM_G8 rows
     int compact_rows = 1;                // option "compact_rows": use NB_WIN_COMPACT
+    int claim_list = 1;                  // option "claim_list": k_num_hash_list for the 1 024 / 4 096-slot bins
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
     std::string err;
@@ -459,6 +460,13 @@ int launch_symbolic_bins(mhb_context *h)
 }
 
 // ---- family 4 launches ------------------------------------------------------------------
+// shared memory of k_num_hash_list for a table of S slots (see the layout in the kernel)
+template <typename T>
+size_t hash_list_smem(int S)
+{
+    return (size_t)S * (sizeof(T) + 4) + (size_t)(S / 4 + 3) * 4 + (size_t)(S / 8) * 5 * 2 * 2 + 16;
+}
+
 template <typename T>
 int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv)
 {
@@ -503,9 +511,14 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     if ((n = n_of(NB_H_BLOCK_S)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_S_SLOTS),
-               (unsigned char *)nullptr, 0LL, scal);
+        if (h->claim_list)
+            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks), 256, hash_list_smem<T>(NB_H_BLOCK_S_SLOTS),
+                      bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      log2_ceil(NB_H_BLOCK_S_SLOTS), scal);
+        else
+            LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
+                      bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
     {
@@ -516,12 +529,16 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     }
     if ((n = n_of(NB_H_WARP_L)) > 0)
     {
-        // 1 024-slot tables: 12 KB each, so only ~18 fit an SM.  Two warps share one table
-        // (block kernel, 64 threads) to keep ~36 warps resident instead of 18.
+        // 1 024-slot tables: two warps share one table (64 threads) so that ~28-36 warps stay resident
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
-                  bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
-                  (unsigned char *)nullptr, 0LL, scal);
+        if (h->claim_list)
+            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 4), 64, hash_list_smem<T>(NB_H_WARP_L_SLOTS),
+                      bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
+                      scal);
+        else
+            LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
+                      bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      log2_ceil(NB_H_WARP_L_SLOTS), (unsigned char *)nullptr, 0LL, scal);
     }
     if ((n = n_of(NB_WIN_COMPACT)) > 0)
     {
@@ -555,21 +572,33 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     }
     if ((n = n_of(NB_H_WARP_M)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+        if (h->claim_list)
+            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_M_SLOTS),
+                      bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+        else
+        {
+            constexpr int G = 32, GPB = kNumGroupThreads / G;
+            auto kern = k_num_hash_group<G, T>;
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+                      GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+        }
     }
     if ((n = n_of(NB_H_WARP_S)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+        if (h->claim_list)
+            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_S_SLOTS),
+                      bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+        else
+        {
+            constexpr int G = 32, GPB = kNumGroupThreads / G;
+            auto kern = k_num_hash_group<G, T>;
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+                      GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+        }
     }
     if ((n = n_of(NB_H_WARP_XS)) > 0)
     {
@@ -617,6 +646,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
+    CU(allow_smem(k_num_hash_list<double>, (int)hash_list_smem<double>(NB_H_BLOCK_S_SLOTS)));
+    CU(allow_smem(k_num_hash_list<float>, (int)hash_list_smem<float>(NB_H_BLOCK_S_SLOTS)));
     CU(allow_smem(k_num_tiny<double>, NB_TINY_MAX * kTinyRowThreads * 12));
     CU(allow_smem(k_num_tiny<float>, NB_TINY_MAX * kTinyRowThreads * 8));
     CU(allow_smem(k_num_compact_rowtwins<double>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 8 + 4 * 100 * 8));
@@ -1000,6 +1031,8 @@ extern "C"
             h->force_sym = (int)value;
         else if (k == "force_num_path")
             h->force_num = (int)value;
+        else if (k == "claim_list")
+            h->claim_list = (int)value;
         else if (k == "compact_rows")
             h->compact_rows = (int)value;
         else if (k == "row_twins")

@@ -1039,6 +1039,203 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
     }
 }
 
+// ---- hash with a claim list: one block per row, table in shared memory ------------------
+// The table is cleared once per block.  A lane that claims an empty slot appends the slot
+// index to a list (one warp-aggregated shared-memory atomicAdd per step), so after the walk
+// the row's entries are known without sweeping the table: no per-row initialisation, no
+// compaction pass (the ballot/scan compaction was ~half of the instructions of
+// k_num_hash_block on rows of a few hundred entries).  The bucket-rank sort runs over the
+// list, emits into C, and the used slots are reset on the way out.
+// smem: vals[S] | keys[S] | start[NB+1] | cursor[NB] | misc[2] | list[5S/8] u16 | idx[5S/8] u16
+template <typename T>
+__global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+                                const int *__restrict__ Ac, const T *__restrict__ Av,
+                                const int *__restrict__ Bp, const int *__restrict__ Bc,
+                                const T *__restrict__ Bv, const int4 *__restrict__ arow,
+                                const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
+                                int *__restrict__ scal)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __shared__ int warp_tot[32];
+    const int S = 1 << logS, NB = S >> 3, nmax = (S >> 3) * 5;
+    T *vals = reinterpret_cast<T *>(sm_raw);
+    int *keys = reinterpret_cast<int *>(vals + S);
+    int *start = keys + S;
+    int *cursor = start + NB + 1;
+    int *misc = cursor + NB; // [0] entries claimed so far
+    unsigned short *list = reinterpret_cast<unsigned short *>(misc + 2);
+    unsigned short *idx = list + nmax;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = lane_id(), nwarp = nthr >> 5;
+    for (int i = tid; i < S; i += nthr)
+    {
+        keys[i] = -1;
+        vals[i] = T(0);
+    }
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x)
+    {
+        const int row = rows[r];
+        const int out = __ldg(&Cp[row]);
+        const int n = __ldg(&Cp[row + 1]) - out;
+        const int4 info = __ldg(&arow[row]);
+        const int cmin = info.z, W = info.w - info.z + 1;
+        const int sh = max(0, ceil_log2_dev(W) - (logS - 3));
+        for (int b = tid; b < NB; b += nthr)
+        {
+            start[b] = 0;
+            cursor[b] = 0;
+        }
+        if (tid == 0)
+            misc[0] = 0;
+        __syncthreads();
+        const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        walk_flat_post<32, T, T>(
+            kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv,
+            [&](int c, T v, T a) {
+                // find-or-claim; report the slot only when this lane claimed it
+                const unsigned S1 = (unsigned)S - 1u;
+                unsigned h = hash_slot((unsigned)c, logS);
+                for (unsigned it = 0; it <= S1; ++it)
+                {
+                    int old = keys[h];
+                    if (old == c)
+                    {
+                        atomicAdd(&vals[h], a * v);
+                        return -1;
+                    }
+                    if (old == -1)
+                    {
+                        old = atomicCAS(&keys[h], -1, c);
+                        if (old == -1 || old == c)
+                        {
+                            atomicAdd(&vals[h], a * v);
+                            return old == -1 ? (int)h : -1;
+                        }
+                    }
+                    h = (h + 1) & S1;
+                }
+                atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+                return -1;
+            },
+            [&](int claimed) {
+                const unsigned cm = __ballot_sync(kFull, claimed >= 0);
+                if (cm)
+                {
+                    const int leader = __ffs(cm) - 1;
+                    int base = 0;
+                    if (lane == leader)
+                        base = atomicAdd(&misc[0], __popc(cm));
+                    base = __shfl_sync(kFull, base, leader);
+                    if (claimed >= 0)
+                    {
+                        const int pos = base + __popc(cm & lanemask_lt());
+                        if (pos < nmax)
+                            list[pos] = (unsigned short)claimed;
+                    }
+                }
+            });
+        __syncthreads();
+        // bucket-rank sort over the claim list (see bucket_sort_emit_warp for the idea)
+        for (int i = tid; i < n; i += nthr)
+            atomicAdd(&start[(keys[list[i]] - cmin) >> sh], 1);
+        __syncthreads();
+        int carry = 0, mx = 0;
+        for (int b0 = 0; b0 < NB; b0 += nthr)
+        {
+            const int b = b0 + tid;
+            const int c = (b < NB) ? start[b] : 0;
+            mx = max(mx, c);
+            int tot;
+            const int ex = block_excl_scan(c, warp_tot, &tot);
+            if (b < NB)
+                start[b] = carry + ex;
+            carry += tot;
+        }
+        if (tid == 0)
+            start[NB] = n;
+        const bool clustered = __syncthreads_or(mx > kBucketMax);
+        if (!clustered)
+        {
+            for (int i = tid; i < n; i += nthr)
+            {
+                const unsigned short sl = list[i];
+                const int b = (keys[sl] - cmin) >> sh;
+                idx[start[b] + atomicAdd(&cursor[b], 1)] = sl;
+            }
+            __syncthreads();
+            for (int p = tid; p < n; p += nthr)
+            {
+                const int sl = idx[p];
+                const int k = keys[sl];
+                const int b = (k - cmin) >> sh;
+                const int lo = start[b], hi = start[b + 1];
+                int rank = lo;
+                for (int q = lo; q < hi; ++q)
+                    rank += keys[idx[q]] < k;
+                Cc[out + rank] = k;
+                Cv[out + rank] = vals[sl];
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += nthr) // leave the table clean for the next row
+            {
+                const int sl = list[i];
+                keys[sl] = -1;
+                vals[sl] = T(0);
+            }
+        }
+        else
+        {
+            // heavily clustered columns: pull the entries into registers, rebuild them as dense
+            // arrays at the front of the table and bitonic-sort there (at most 10 per thread)
+            int rk[10];
+            T rv[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+            {
+                const int i = tid + j * nthr;
+                rk[j] = INT_MAX;
+                rv[j] = T(0);
+                if (i < n)
+                {
+                    const int sl = list[i];
+                    rk[j] = keys[sl];
+                    rv[j] = vals[sl];
+                }
+            }
+            __syncthreads();
+            int P = 2;
+            while (P < n)
+                P <<= 1;
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+            {
+                const int i = tid + j * nthr;
+                if (i < n)
+                {
+                    keys[i] = rk[j];
+                    vals[i] = rv[j];
+                }
+            }
+            for (int i = n + tid; i < P; i += nthr)
+                keys[i] = INT_MAX;
+            __syncthreads();
+            bitonic_sort_kv(keys, vals, P, tid, nthr, [&]() { __syncthreads(); });
+            for (int i = tid; i < n; i += nthr)
+            {
+                Cc[out + i] = keys[i];
+                Cv[out + i] = vals[i];
+            }
+            __syncthreads();
+            for (int i = tid; i < S; i += nthr) // full clear: slots outside [0, P) may still be set
+            {
+                keys[i] = -1;
+                vals[i] = T(0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- tiny rows: one thread per row ------------------------------------------------------
 // n <= NB_TINY_MAX (24) entries and <= NB_TINY_PRODUCTS products.  The thread appends (column,
 // value) pairs to its own shared-memory column (bank = thread, conflict-free), merging

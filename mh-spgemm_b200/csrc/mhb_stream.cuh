@@ -309,4 +309,53 @@ __device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int 
     }
 }
 
+// walk_flat with a convergent hook: update(c, v, a) returns an int per product (e.g. a newly
+// claimed hash slot, or -1); post(r) is then executed by ALL lanes of the group at a
+// convergent point (r = -1 for lanes that had no product), so it may use ballots/shuffles.
+template <int G, typename TA, typename TB, class Update, class Post>
+__device__ __forceinline__ void walk_flat_post(unsigned gm, int l, int s, int e, int tpart, int tparts,
+                                               const int *__restrict__ Ac, const TA *__restrict__ Av,
+                                               const int *__restrict__ Bp, const int *__restrict__ Bc,
+                                               const TB *__restrict__ Bv, Update update, Post post)
+{
+    int bs, be, nbs, nbe;
+    TA av, nav;
+    load_meta<TA>(s + l, e, Ac, Av, Bp, bs, be, av);
+    for (int j0 = s; j0 < e; j0 += G)
+    {
+        load_meta<TA>(j0 + G + l, e, Ac, Av, Bp, nbs, nbe, nav);
+        const int len = be - bs;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1)
+        {
+            const int t = __shfl_up_sync(gm, incl, o, G);
+            if (l >= o)
+                incl += t;
+        }
+        const int off = incl - len;
+        const int total = __shfl_sync(gm, incl, G - 1, G);
+        const int base = bs - off;
+        for (int t0 = tpart * G; t0 < total; t0 += tparts * G)
+        {
+            const int t = t0 + l;
+            int ent = 0;
+#pragma unroll
+            for (int step = G / 2; step > 0; step >>= 1)
+            {
+                const int o = __shfl_sync(gm, off, ent + step, G);
+                if (o <= t)
+                    ent += step;
+            }
+            const int q = t + __shfl_sync(gm, base, ent, G);
+            const TA a = group_bcast<TA>(gm, av, ent, G);
+            int r = -1;
+            if (t < total)
+                r = update(__ldg(&Bc[q]), __ldg(&Bv[q]), a);
+            post(r);
+        }
+        bs = nbs, be = nbe, av = nav;
+    }
+}
+
 } // namespace mhb
