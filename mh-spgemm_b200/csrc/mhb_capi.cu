@@ -602,12 +602,18 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     }
     if ((n = n_of(NB_H_WARP_XS)) > 0)
     {
-        constexpr int G = 32, GPB = kNumGroupThreads / G;
-        auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-               Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
+        if (h->claim_list)
+            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_XS_SLOTS),
+                      bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
+        else
+        {
+            constexpr int G = 32, GPB = kNumGroupThreads / G;
+            auto kern = k_num_hash_group<G, T>;
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
+                      GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
+        }
     }
     if ((n = n_of(NB_WIN_G8)) > 0)
     {
