@@ -301,7 +301,7 @@ def main():
 
     for _ in range(args.warmup):
         out = one_step()
-    nnzC_total = int(out[4])
+    nnzC_total = out[4].offsets()[1] if hasattr(out[4], "offsets") else int(out[4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -98,6 +98,36 @@ def slice_offsets(nnz_local: int, rank: int, world: int, device, on_host: bool =
     return int(sizes[:rank].sum()), int(sizes.sum())
 
 
+class SliceSizes:
+    """Per-step all-gather of the ranks' nnz(C slice) with preallocated buffers: one small
+    non-blocking H2D from pinned memory and one NCCL all-gather; the exclusive prefix (the
+    slice offsets of the global CSR) is taken lazily by whoever assembles C."""
+
+    def __init__(self, rank: int, world: int, device):
+        import torch
+        self.rank, self.world = rank, world
+        if world > 1:
+            self.host = torch.zeros(1, dtype=torch.int64).pin_memory() if device.type == "cuda" else torch.zeros(1, dtype=torch.int64)
+            self.mine = torch.zeros(1, dtype=torch.int64, device=device)
+            self.all = torch.zeros(world, dtype=torch.int64, device=device)
+
+    def gather(self, nnz_local: int):
+        import torch.distributed as dist
+        self.nnz = int(nnz_local)
+        if self.world > 1:
+            self.host[0] = self.nnz
+            self.mine.copy_(self.host, non_blocking=True)
+            dist.all_gather_into_tensor(self.all, self.mine)
+        return self
+
+    def offsets(self):
+        """(offset of this rank's slice, total nnz(C)) on the host (synchronises)."""
+        if self.world == 1:
+            return 0, self.nnz
+        sizes = self.all.cpu().numpy()
+        return int(sizes[:self.rank].sum()), int(sizes.sum())
+
+
 class RangeExchange:
     """B exchange when B is row-sharded like A (the natural layout for C = A*A): rank r owns
     B rows [bounds[r], bounds[r+1]) and needs the rows [k0, k1) that the columns of its A
@@ -181,6 +211,7 @@ class ShardedSpGEMM:
         import torch
         self.tool, self.rank, self.world = tool, rank, world
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.sizes = SliceSizes(rank, world, self.device)
 
     def step(self, A_blk, Bbuf, K: int, N: int, nnzB: int, val_dtype, src: int = 0):
         """One sharded SpGEMM.  A_blk = (M_local, ptr, col, val) device tensors of this
@@ -208,7 +239,10 @@ class ShardedSpGEMM:
         ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
         cval = torch.empty(max(nnz, 1), dtype=val_dtype, device=self.device)
         self.tool.numeric_into(av, bv, ccol, cval)
-        off, total = slice_offsets(nnz, self.rank, self.world, self.device, on_host=offsets_on_host)
+        if offsets_on_host:
+            off, total = slice_offsets(nnz, self.rank, self.world, self.device, on_host=True)
+        else:  # sizes stay on the device; SliceSizes.offsets() turns them into offsets on demand
+            off, total = None, self.sizes.gather(nnz)
         return cp, ccol[:nnz], cval[:nnz], off, total
 
 
