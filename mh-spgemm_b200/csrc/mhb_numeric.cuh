@@ -289,6 +289,47 @@ __global__ void __launch_bounds__(kRowTwinThreads)
     }
 }
 
+// One step of the rank-mapped kernel: up to kPre*32 entries of a B row (and of its one or two
+// folded twins) held in registers.
+template <typename T>
+struct CompactStep
+{
+    int c[kPre];                     // column per chunk, -1 = lane idle
+    T v0[kPre], v1[kPre], v2[kPre];  // values of the B row and of its folded twins
+    int q, qe, sz, o1, o2, ci;       // entry range, folded rows (1..3), twin offsets, index into the A stage
+};
+
+// acc_r[rank] += sum_j a[r][j] * b_j for R twin rows of A and SZ folded rows of B.  The ranks of
+// one step are distinct (distinct columns of one B row), so all loads may precede all stores.
+template <typename T, int R, int SZ>
+__device__ __forceinline__ void compact_accumulate(T *acc0, int ncap, const T *sa, int SG, const int (&rk)[kPre],
+                                                   const bool (&act)[kPre], const CompactStep<T> &P)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+    {
+        const T a0 = sa[r * SG];
+        const T a1 = (SZ > 1) ? sa[r * SG + 1] : T(0);
+        const T a2 = (SZ > 2) ? sa[r * SG + 2] : T(0);
+        T *acc = acc0 + r * ncap;
+        T v[kPre], o[kPre];
+#pragma unroll
+        for (int t = 0; t < kPre; ++t)
+        {
+            v[t] = a0 * P.v0[t];
+            if (SZ > 1)
+                v[t] = fma(a1, P.v1[t], v[t]);
+            if (SZ > 2)
+                v[t] = fma(a2, P.v2[t], v[t]);
+            o[t] = acc[rk[t]];
+        }
+#pragma unroll
+        for (int t = 0; t < kPre; ++t)
+            if (act[t])
+                acc[rk[t]] = o[t] + v[t];
+    }
+}
+
 // =========================================================================================
 // Rank-mapped ("compact") window, one warp per group of up to three twin rows of A.
 // The symbolic pass kept the occupancy bitmap of these rows (bm_store, <= 64 words).  A warp
@@ -399,33 +440,36 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                 const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
                 const unsigned fmask = __ballot_sync(kFull, fol);
                 __syncwarp();
-                int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0, ni = 0;
-                T pv0[kPre], pv1[kPre], pv2[kPre];
-                auto issue = [&](int i) {
-                    ni = i;
-                    nsz = 1 + ((fmask >> (i + 1)) & 1u);
-                    if (nsz == 2)
-                        nsz += (fmask >> (i + 2)) & 1u;
-                    if (i + nsz > cnt)
-                        nsz = cnt - i;
+                // two register sets: while one B-row step is accumulated the loads of the next are in flight
+                CompactStep<T> PA, PB;
+                auto issue = [&](CompactStep<T> &P, int i) {
+                    P.ci = i;
+                    int sz = 1 + ((fmask >> (i + 1)) & 1u);
+                    if (sz == 2)
+                        sz += (fmask >> (i + 2)) & 1u;
+                    if (i + sz > cnt)
+                        sz = cnt - i;
+                    P.sz = sz;
                     const int2 e0 = stage_be[i], e1 = stage_be[i + 1], e2 = stage_be[i + 2];
-                    nq = e0.x;
-                    nqe = e0.y;
-                    nb1 = e1.x - nq;
-                    nb2 = e2.x - nq;
+                    P.q = e0.x;
+                    P.qe = e0.y;
+                    P.o1 = e1.x - e0.x;
+                    P.o2 = e2.x - e0.x;
+                    const int *pcol = Bc + e0.x + l;
+                    const T *p0 = Bv + e0.x + l, *p1 = p0 + P.o1, *p2 = p0 + P.o2;
+                    const int left = e0.y - e0.x - l; // entries of the B row at or behind this lane
 #pragma unroll
                     for (int t = 0; t < kPre; ++t)
                     {
-                        const int p = nq + t * G + l;
-                        pc[t] = -1;
-                        if (p < nqe)
+                        P.c[t] = -1;
+                        if (t * G < left)
                         {
-                            pc[t] = __ldg(&Bc[p]);
-                            pv0[t] = __ldg(&Bv[p]);
-                            if (nsz > 1)
-                                pv1[t] = __ldg(&Bv[p + nb1]);
-                            if (nsz > 2)
-                                pv2[t] = __ldg(&Bv[p + nb2]);
+                            P.c[t] = __ldg(pcol + t * G);
+                            P.v0[t] = __ldg(p0 + t * G);
+                            if (sz > 1)
+                                P.v1[t] = __ldg(p1 + t * G);
+                            if (sz > 2)
+                                P.v2[t] = __ldg(p2 + t * G);
                         }
                     }
                 };
@@ -433,56 +477,81 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                     const uint2 w = lut[(c >> MHB_TILE_SHIFT) - tbase];
                     return (int)w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
                 };
-                issue(0);
-                for (int i = 0; i < cnt;)
-                {
+                auto consume = [&](const CompactStep<T> &P) {
                     int rk[kPre];
-                    T b0[kPre], b1[kPre], b2[kPre];
                     bool act[kPre];
-                    const int q = nq, qe = nqe, sz = nsz, o1 = nb1, o2 = nb2, ci = ni;
 #pragma unroll
                     for (int t = 0; t < kPre; ++t)
                     {
-                        act[t] = pc[t] >= 0;
-                        rk[t] = act[t] ? rank_of(pc[t]) : 0; // idle lanes point at entry 0 and store nothing
-                        b0[t] = pv0[t], b1[t] = pv1[t], b2[t] = pv2[t];
+                        act[t] = P.c[t] >= 0;
+                        rk[t] = act[t] ? rank_of(P.c[t]) : 0; // idle lanes point at entry 0 and store nothing
                     }
-                    i += sz;
-                    if (i < cnt)
-                        issue(i);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
+                    const T *sa = stage_a + P.ci;
+                    // straight-line code for every (twin rows of A) x (folded rows of B) shape
+                    if (R == 3)
                     {
-                        if (r >= R)
-                            break;
-                        const T a0 = stage_a[r * SG + ci];
-                        const T a1 = (sz > 1) ? stage_a[r * SG + ci + 1] : T(0);
-                        const T a2 = (sz > 2) ? stage_a[r * SG + ci + 2] : T(0);
-                        T *acc = acc0 + r * ncap;
-#pragma unroll
-                        for (int t = 0; t < kPre; ++t)
+                        if (P.sz == 3)
+                            compact_accumulate<T, 3, 3>(acc0, ncap, sa, SG, rk, act, P);
+                        else if (P.sz == 2)
+                            compact_accumulate<T, 3, 2>(acc0, ncap, sa, SG, rk, act, P);
+                        else
+                            compact_accumulate<T, 3, 1>(acc0, ncap, sa, SG, rk, act, P);
+                    }
+                    else if (R == 2)
+                    {
+                        if (P.sz == 3)
+                            compact_accumulate<T, 2, 3>(acc0, ncap, sa, SG, rk, act, P);
+                        else if (P.sz == 2)
+                            compact_accumulate<T, 2, 2>(acc0, ncap, sa, SG, rk, act, P);
+                        else
+                            compact_accumulate<T, 2, 1>(acc0, ncap, sa, SG, rk, act, P);
+                    }
+                    else
+                    {
+                        if (P.sz == 3)
+                            compact_accumulate<T, 1, 3>(acc0, ncap, sa, SG, rk, act, P);
+                        else if (P.sz == 2)
+                            compact_accumulate<T, 1, 2>(acc0, ncap, sa, SG, rk, act, P);
+                        else
+                            compact_accumulate<T, 1, 1>(acc0, ncap, sa, SG, rk, act, P);
+                    }
+                    if (P.qe - P.q > kPre * G) // B rows longer than kPre*G (warp-uniform, rare)
+                    {
+                        for (int r = 0; r < R; ++r)
                         {
-                            T v = a0 * b0[t];
-                            if (sz > 1)
-                                v = fma(a1, b1[t], v);
-                            if (sz > 2)
-                                v = fma(a2, b2[t], v);
-                            const T o = acc[rk[t]];
-                            if (act[t])
-                                acc[rk[t]] = o + v; // columns of one step are distinct: no atomic
-                        }
-                        for (int p = q + kPre * G + l; p < qe; p += G) // B rows longer than kPre*G
-                        {
-                            T v = a0 * __ldg(&Bv[p]);
-                            if (sz > 1)
-                                v = fma(a1, __ldg(&Bv[p + o1]), v);
-                            if (sz > 2)
-                                v = fma(a2, __ldg(&Bv[p + o2]), v);
-                            const int k = rank_of(__ldg(&Bc[p]));
-                            acc[k] += v;
+                            const T a0 = sa[r * SG];
+                            const T a1 = (P.sz > 1) ? sa[r * SG + 1] : T(0);
+                            const T a2 = (P.sz > 2) ? sa[r * SG + 2] : T(0);
+                            T *acc = acc0 + r * ncap;
+                            for (int p = P.q + kPre * G + l; p < P.qe; p += G)
+                            {
+                                T v = a0 * __ldg(&Bv[p]);
+                                if (P.sz > 1)
+                                    v = fma(a1, __ldg(&Bv[p + P.o1]), v);
+                                if (P.sz > 2)
+                                    v = fma(a2, __ldg(&Bv[p + P.o2]), v);
+                                const int k = rank_of(__ldg(&Bc[p]));
+                                acc[k] += v;
+                            }
                         }
                     }
                     __syncwarp();
+                };
+                issue(PA, 0);
+                for (int i = 0;;)
+                {
+                    i += PA.sz;
+                    if (i < cnt)
+                        issue(PB, i);
+                    consume(PA);
+                    if (i >= cnt)
+                        break;
+                    i += PB.sz;
+                    if (i < cnt)
+                        issue(PA, i);
+                    consume(PB);
+                    if (i >= cnt)
+                        break;
                 }
                 bs = nbs, be = nbe, kk = nkk, av0 = nav0, av1 = nav1, av2 = nav2;
             }
