@@ -1110,12 +1110,14 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
 
 // ---- hash with a claim list: one block per row, table in shared memory ------------------
 // The table is cleared once per block.  A lane that claims an empty slot appends the slot
-// index to a list (one warp-aggregated shared-memory atomicAdd per step), so after the walk
-// the row's entries are known without sweeping the table: no per-row initialisation, no
-// compaction pass (the ballot/scan compaction was ~half of the instructions of
-// k_num_hash_block on rows of a few hundred entries).  The bucket-rank sort runs over the
-// list, emits into C, and the used slots are reset on the way out.
-// smem: vals[S] | keys[S] | start[NB+1] | cursor[NB] | misc[2] | list[5S/8] u16 | idx[5S/8] u16
+// index to a list (one warp-aggregated shared-memory atomicAdd per step) and counts the key
+// into its column bucket, so after the walk the row's entries and the bucket histogram are
+// known without sweeping the table: no per-row initialisation, no compaction pass, no
+// histogram pass.  The probe loop only finds the slot; the value is added once, after the
+// lanes have reconverged (one LDS/DADD/CAS sequence per step instead of one per divergent
+// path).  The bucket-rank sort (S/4 buckets: ~2 keys per bucket) scatters (slot, key) pairs,
+// ranks each key inside its bucket, emits into C and resets the slot on the way out.
+// smem: vals[S] | keys[S] | start[NB+1] | misc[3] | bkey[5S/8] | list[5S/8] u16 | idx[5S/8] u16
 template <typename T>
 __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                                 const int *__restrict__ Ac, const T *__restrict__ Av,
@@ -1126,14 +1128,14 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
-    const int S = 1 << logS, NB = S >> 3, nmax = (S >> 3) * 5;
+    const int S = 1 << logS, NB = S >> 2, nmax = (S >> 3) * 5;
     T *vals = reinterpret_cast<T *>(sm_raw);
     int *keys = reinterpret_cast<int *>(vals + S);
-    int *start = keys + S;
-    int *cursor = start + NB + 1;
-    int *misc = cursor + NB; // [0] entries claimed so far
-    unsigned short *list = reinterpret_cast<unsigned short *>(misc + 2);
-    unsigned short *idx = list + nmax;
+    int *start = keys + S;      // [NB + 1] bucket counts -> bucket begins -> bucket ends
+    int *misc = start + NB + 1; // [0] entries claimed so far
+    int *bkey = misc + 3;       // keys in bucket order
+    unsigned short *list = reinterpret_cast<unsigned short *>(bkey + nmax);
+    unsigned short *idx = list + nmax; // slots in bucket order
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = lane_id(), nwarp = nthr >> 5;
     for (int i = tid; i < S; i += nthr)
@@ -1148,12 +1150,9 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
         const int n = __ldg(&Cp[row + 1]) - out;
         const int4 info = __ldg(&arow[row]);
         const int cmin = info.z, W = info.w - info.z + 1;
-        const int sh = max(0, ceil_log2_dev(W) - (logS - 3));
-        for (int b = tid; b < NB; b += nthr)
-        {
+        const int sh = max(0, ceil_log2_dev(W) - (logS - 2));
+        for (int b = tid; b <= NB; b += nthr)
             start[b] = 0;
-            cursor[b] = 0;
-        }
         if (tid == 0)
             misc[0] = 0;
         __syncthreads();
@@ -1161,30 +1160,32 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
         walk_flat_post<32, T, T>(
             kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv,
             [&](int c, T v, T a) {
-                // find-or-claim; report the slot only when this lane claimed it
+                // find-or-claim, all lanes in lockstep (c < 0: nothing to insert): the loop leaves
+                // when every lane has its slot, so the value update below runs once per step
                 const unsigned S1 = (unsigned)S - 1u;
                 unsigned h = hash_slot((unsigned)c, logS);
-                for (unsigned it = 0; it <= S1; ++it)
+                int claimed = -1;
+                bool need = c >= 0;
+                for (unsigned it = 0; it <= S1 && __any_sync(kFull, need); ++it)
                 {
-                    int old = keys[h];
-                    if (old == c)
+                    if (need)
                     {
-                        atomicAdd(&vals[h], a * v);
-                        return -1;
-                    }
-                    if (old == -1)
-                    {
-                        old = atomicCAS(&keys[h], -1, c);
+                        const int old = atomicCAS(&keys[h], -1, c);
+                        if (old == -1)
+                            claimed = (int)h;
                         if (old == -1 || old == c)
-                        {
-                            atomicAdd(&vals[h], a * v);
-                            return old == -1 ? (int)h : -1;
-                        }
+                            need = false;
+                        else
+                            h = (h + 1) & S1;
                     }
-                    h = (h + 1) & S1;
                 }
-                atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
-                return -1;
+                if (need) // S probes without a home: the row has more entries than symbolic promised
+                    atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+                else if (c >= 0)
+                    atomicAdd(&vals[h], a * v);
+                if (claimed >= 0)
+                    atomicAdd(&start[(c - cmin) >> sh], 1);
+                return claimed;
             },
             [&](int claimed) {
                 const unsigned cm = __ballot_sync(kFull, claimed >= 0);
@@ -1204,51 +1205,57 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                 }
             });
         __syncthreads();
-        // bucket-rank sort over the claim list (see bucket_sort_emit_warp for the idea)
-        for (int i = tid; i < n; i += nthr)
-            atomicAdd(&start[(keys[list[i]] - cmin) >> sh], 1);
-        __syncthreads();
+        // bucket counts -> bucket begins (see bucket_sort_emit_warp for the idea of the sort)
         int carry = 0, mx = 0;
         for (int b0 = 0; b0 < NB; b0 += nthr)
         {
             const int b = b0 + tid;
             const int c = (b < NB) ? start[b] : 0;
             mx = max(mx, c);
-            int tot;
-            const int ex = block_excl_scan(c, warp_tot, &tot);
+            int tot, ex;
+            if (nthr == 32)
+            {
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o)
+                        incl += t;
+                }
+                ex = incl - c;
+                tot = __shfl_sync(kFull, incl, 31);
+            }
+            else
+                ex = block_excl_scan(c, warp_tot, &tot);
             if (b < NB)
                 start[b] = carry + ex;
             carry += tot;
         }
-        if (tid == 0)
-            start[NB] = n;
         const bool clustered = __syncthreads_or(mx > kBucketMax);
         if (!clustered)
         {
             for (int i = tid; i < n; i += nthr)
             {
                 const unsigned short sl = list[i];
-                const int b = (keys[sl] - cmin) >> sh;
-                idx[start[b] + atomicAdd(&cursor[b], 1)] = sl;
+                const int k = keys[sl];
+                const int pos = atomicAdd(&start[(k - cmin) >> sh], 1); // start[b] ends as the END of bucket b
+                idx[pos] = sl;
+                bkey[pos] = k;
             }
             __syncthreads();
             for (int p = tid; p < n; p += nthr)
             {
                 const int sl = idx[p];
-                const int k = keys[sl];
+                const int k = bkey[p];
                 const int b = (k - cmin) >> sh;
-                const int lo = start[b], hi = start[b + 1];
+                const int lo = b ? start[b - 1] : 0, hi = start[b];
                 int rank = lo;
                 for (int q = lo; q < hi; ++q)
-                    rank += keys[idx[q]] < k;
+                    rank += bkey[q] < k;
                 Cc[out + rank] = k;
                 Cv[out + rank] = vals[sl];
-            }
-            __syncthreads();
-            for (int i = tid; i < n; i += nthr) // leave the table clean for the next row
-            {
-                const int sl = list[i];
-                keys[sl] = -1;
+                keys[sl] = -1; // leave the table clean for the next row
                 vals[sl] = T(0);
             }
         }

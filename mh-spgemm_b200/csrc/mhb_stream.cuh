@@ -309,9 +309,10 @@ __device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int 
     }
 }
 
-// walk_flat with a convergent hook: update(c, v, a) returns an int per product (e.g. a newly
-// claimed hash slot, or -1); post(r) is then executed by ALL lanes of the group at a
-// convergent point (r = -1 for lanes that had no product), so it may use ballots/shuffles.
+// walk_flat with convergent hooks: update(c, v, a) is executed by ALL lanes of the group
+// (c = -1 for lanes that have no product in this step) and returns an int per product (e.g. a
+// newly claimed hash slot, or -1); post(r) follows, also convergent, so both may use
+// ballots/shuffles.  The B entries of a step are loaded one step before they are used.
 template <int G, typename TA, typename TB, class Update, class Post>
 __device__ __forceinline__ void walk_flat_post(unsigned gm, int l, int s, int e, int tpart, int tparts,
                                                const int *__restrict__ Ac, const TA *__restrict__ Av,
@@ -336,9 +337,8 @@ __device__ __forceinline__ void walk_flat_post(unsigned gm, int l, int s, int e,
         const int off = incl - len;
         const int total = __shfl_sync(gm, incl, G - 1, G);
         const int base = bs - off;
-        for (int t0 = tpart * G; t0 < total; t0 += tparts * G)
-        {
-            const int t = t0 + l;
+        // item t of the chunk -> (entry of A it belongs to, position in B); one step ahead of its use
+        auto fetch = [&](int t, int &c, TB &v, TA &a) {
             int ent = 0;
 #pragma unroll
             for (int step = G / 2; step > 0; step >>= 1)
@@ -348,11 +348,28 @@ __device__ __forceinline__ void walk_flat_post(unsigned gm, int l, int s, int e,
                     ent += step;
             }
             const int q = t + __shfl_sync(gm, base, ent, G);
-            const TA a = group_bcast<TA>(gm, av, ent, G);
-            int r = -1;
+            a = group_bcast<TA>(gm, av, ent, G);
+            c = -1;
             if (t < total)
-                r = update(__ldg(&Bc[q]), __ldg(&Bv[q]), a);
+            {
+                c = __ldg(&Bc[q]);
+                v = __ldg(&Bv[q]);
+            }
+        };
+        int cc = -1, nc = -1;
+        TB cv, nv;
+        TA ca, na;
+        int t0 = tpart * G;
+        if (t0 < total)
+            fetch(t0 + l, cc, cv, ca);
+        for (; t0 < total; t0 += tparts * G)
+        {
+            nc = -1;
+            if (t0 + tparts * G < total)
+                fetch(t0 + tparts * G + l, nc, nv, na);
+            const int r = update(cc, cv, ca); // ALL lanes; cc = -1 marks a lane without a product
             post(r);
+            cc = nc, cv = nv, ca = na;
         }
         bs = nbs, be = nbe, av = nav;
     }
