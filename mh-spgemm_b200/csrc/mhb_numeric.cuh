@@ -1115,7 +1115,11 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
 // known without sweeping the table: no per-row initialisation, no compaction pass, no
 // histogram pass.  The probe loop only finds the slot; the value is added once, after the
 // lanes have reconverged (one LDS/DADD/CAS sequence per step instead of one per divergent
-// path).  The bucket-rank sort (S/4 buckets: ~2 keys per bucket) scatters (slot, key) pairs,
+// path).  fp64 atomicAdd on shared memory is a CAS loop that costs ~2 LSU wavefronts per LANE
+// (ncu: a third of the kernel's shared-memory traffic), so a single-warp block avoids it where
+// it can: the lane that claimed a slot owns its first value and writes it with a plain store
+// (which also makes zeroing the values unnecessary); only lanes that hit an existing key add
+// atomically, after a __syncwarp, and rows with little compression have almost none of those.  The bucket-rank sort (S/4 buckets: ~2 keys per bucket) scatters (slot, key) pairs,
 // ranks each key inside its bucket, emits into C and resets the slot on the way out.
 // smem: vals[S] | keys[S] | start[NB+1] | misc[3] | bkey[5S/8] | list[5S/8] u16 | idx[5S/8] u16
 template <typename T>
@@ -1138,6 +1142,7 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
     unsigned short *idx = list + nmax; // slots in bucket order
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = lane_id(), nwarp = nthr >> 5;
+    const bool solo = nthr == 32; // one warp: claimed slots are written, not added to
     for (int i = tid; i < S; i += nthr)
     {
         keys[i] = -1;
@@ -1168,21 +1173,33 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                 bool need = c >= 0;
                 for (unsigned it = 0; it <= S1 && __any_sync(kFull, need); ++it)
                 {
+                    int old = -2;
                     if (need)
-                    {
-                        const int old = atomicCAS(&keys[h], -1, c);
-                        if (old == -1)
-                            claimed = (int)h;
-                        if (old == -1 || old == c)
-                            need = false;
-                        else
-                            h = (h + 1) & S1;
-                    }
+                        old = atomicCAS(&keys[h], -1, c);
+                    if (old == -1)
+                        claimed = (int)h;
+                    need = need && old != -1 && old != c;
+                    if (need)
+                        h = (h + 1) & S1;
                 }
                 if (need) // S probes without a home: the row has more entries than symbolic promised
                     atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
-                else if (c >= 0)
-                    atomicAdd(&vals[h], a * v);
+                const bool ok = c >= 0 && !need;
+                if (!solo)
+                {
+                    if (ok)
+                        atomicAdd(&vals[h], a * v);
+                }
+                else
+                {
+                    if (claimed >= 0)
+                        vals[h] = a * v;
+                    __syncwarp();
+                    const bool hit = ok && claimed < 0;
+                    if (__any_sync(kFull, hit))
+                        if (hit)
+                            atomicAdd(&vals[h], a * v);
+                }
                 if (claimed >= 0)
                     atomicAdd(&start[(c - cmin) >> sh], 1);
                 return claimed;
@@ -1256,7 +1273,8 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                 Cc[out + rank] = k;
                 Cv[out + rank] = vals[sl];
                 keys[sl] = -1; // leave the table clean for the next row
-                vals[sl] = T(0);
+                if (!solo)
+                    vals[sl] = T(0);
             }
         }
         else

@@ -217,6 +217,33 @@ __device__ __forceinline__ void tile_insert(int *keys, unsigned *masks, int logS
     atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
 }
 
+// The same insertion with the lanes of a group in lockstep (tc < 0: nothing to insert): the
+// probe loop leaves when every lane has its slot, so the mask update runs once per step
+// instead of once per divergent exit path.  Must be called by ALL lanes of `gm`.
+__device__ __forceinline__ int tile_insert_lockstep(unsigned gm, int *keys, unsigned *masks, int logS, int tc,
+                                                    unsigned m, int *scal)
+{
+    const unsigned S1 = (1u << logS) - 1u;
+    unsigned h = hash_slot((unsigned)tc, logS);
+    bool more = tc >= 0;
+    for (unsigned it = 0; it <= S1 && __any_sync(gm, more); ++it)
+    {
+        if (more)
+        {
+            const int old = atomicCAS(&keys[h], -1, tc);
+            if (old == -1 || old == tc)
+                more = false;
+            else
+                h = (h + 1) & S1;
+        }
+    }
+    if (more)
+        atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
+    else if (tc >= 0)
+        atomicOr(&masks[h], m);
+    return -1;
+}
+
 template <int G>
 __global__ void __launch_bounds__(kSymThreads)
     k_sym_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
@@ -241,10 +268,10 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncwarp(gm);
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<G, NoVal, unsigned>(gm, l, s, e, 0, 1, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
-                                      [&](int tc, unsigned m, NoVal) {
-                                          tile_insert<true>(keys, masks, logS, tc, m, scal);
-                                      });
+        walk_flat_post<G, NoVal, unsigned>(
+            gm, l, s, e, 0, 1, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
+            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(gm, keys, masks, logS, tc, m, scal); },
+            [](int) {});
         __syncwarp(gm);
         int c = 0;
         for (int w = l; w < S; w += G)
@@ -295,10 +322,10 @@ __global__ void __launch_bounds__(kSymThreads)
         }
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        walk_flat<32, NoVal, unsigned>(kFull, lane, s, e, warp, nwarp, Ac, (const NoVal *)nullptr,
-                                       tileptr, tilecol, tilemask, [&](int tc, unsigned m, NoVal) {
-                                           tile_insert<true>(keys, masks, logS, tc, m, scal);
-                                       });
+        walk_flat_post<32, NoVal, unsigned>(
+            kFull, lane, s, e, warp, nwarp, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
+            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(kFull, keys, masks, logS, tc, m, scal); },
+            [](int) {});
         __syncthreads();
         int c = 0;
         for (int w = threadIdx.x; w < S; w += blockDim.x)
