@@ -464,7 +464,7 @@ int launch_symbolic_bins(mhb_context *h)
 template <typename T>
 size_t hash_list_smem(int S)
 {
-    return (size_t)S * (sizeof(T) + 4) + (size_t)(S / 4 + 4) * 4 + (size_t)(S / 8) * 5 * (4 + 2 + 2) + 16;
+    return ((size_t)S * (sizeof(T) + 4) + (size_t)(S / 4 + 4) * 4 + (size_t)(S / 8) * 5 * (4 + 2 + 2) + 15) / 16 * 16;
 }
 
 template <typename T>
@@ -512,9 +512,10 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks), 256, hash_list_smem<T>(NB_H_BLOCK_S_SLOTS),
+            { auto kern = k_num_hash_list<T, false>;
+            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks), 256, hash_list_smem<T>(NB_H_BLOCK_S_SLOTS),
                       bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-                      log2_ceil(NB_H_BLOCK_S_SLOTS), scal);
+                      log2_ceil(NB_H_BLOCK_S_SLOTS), scal, 0); }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
@@ -532,9 +533,10 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         // 1 024-slot tables: two warps share one table (64 threads) so that ~28-36 warps stay resident
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 4), 64, hash_list_smem<T>(NB_H_WARP_L_SLOTS),
+            { auto kern = k_num_hash_list<T, false>;
+            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks * 4), 64, hash_list_smem<T>(NB_H_WARP_L_SLOTS),
                       bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
-                      scal);
+                      scal, 0); }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
@@ -574,8 +576,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_M_SLOTS),
-                      bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+            { auto kern = k_num_hash_list<T, false>;
+            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_M_SLOTS),
+                      bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal, 0); }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -589,8 +592,10 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_S_SLOTS),
-                      bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+            { auto kern = k_num_hash_list<T, true>; // four rows (warps) per block
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, 4), cap_blocks * 2), 128, 4 * hash_list_smem<T>(NB_H_WARP_S_SLOTS),
+                      bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal,
+                      (int)hash_list_smem<T>(NB_H_WARP_S_SLOTS)); }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -604,8 +609,10 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            LAUNCH_ON(h, st, k_num_hash_list<T>, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_XS_SLOTS),
-                      bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
+            { auto kern = k_num_hash_list<T, true>; // four rows (warps) per block
+            LAUNCH_ON(h, st, kern, std::min(cdiv(n, 4), cap_blocks * 2), 128, 4 * hash_list_smem<T>(NB_H_WARP_XS_SLOTS),
+                      bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal,
+                      (int)hash_list_smem<T>(NB_H_WARP_XS_SLOTS)); }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -652,8 +659,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
-    CU(allow_smem(k_num_hash_list<double>, (int)hash_list_smem<double>(NB_H_BLOCK_S_SLOTS)));
-    CU(allow_smem(k_num_hash_list<float>, (int)hash_list_smem<float>(NB_H_BLOCK_S_SLOTS)));
+    CU(allow_smem(k_num_hash_list<double, false>, (int)hash_list_smem<double>(NB_H_BLOCK_S_SLOTS)));
+    CU(allow_smem(k_num_hash_list<float, false>, (int)hash_list_smem<float>(NB_H_BLOCK_S_SLOTS)));
     CU(allow_smem(k_num_tiny<double>, NB_TINY_MAX * kTinyRowThreads * 12));
     CU(allow_smem(k_num_tiny<float>, NB_TINY_MAX * kTinyRowThreads * 8));
     CU(allow_smem(k_num_compact_rowtwins<double>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 8 + 4 * 100 * 8));

@@ -1121,34 +1121,47 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
 // (which also makes zeroing the values unnecessary); only lanes that hit an existing key add
 // atomically, after a __syncwarp, and rows with little compression have almost none of those.  The bucket-rank sort (S/4 buckets: ~2 keys per bucket) scatters (slot, key) pairs,
 // ranks each key inside its bucket, emits into C and resets the slot on the way out.
+// WROWS: every WARP of the block owns a row and a table of its own (table_bytes apart) and
+// synchronises with __syncwarp only -- for the small tables this lifts the 32-blocks-per-SM
+// limit of one-warp blocks (32 -> 48..64 resident warps), which is what a latency-bound
+// kernel needs.
 // smem: vals[S] | keys[S] | start[NB+1] | misc[3] | bkey[5S/8] | list[5S/8] u16 | idx[5S/8] u16
-template <typename T>
-__global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+template <typename T, bool WROWS>
+__global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash_list(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                                 const int *__restrict__ Ac, const T *__restrict__ Av,
                                 const int *__restrict__ Bp, const int *__restrict__ Bc,
                                 const T *__restrict__ Bv, const int4 *__restrict__ arow,
                                 const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
-                                int *__restrict__ scal)
+                                int *__restrict__ scal, int table_bytes)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
     const int S = 1 << logS, NB = S >> 2, nmax = (S >> 3) * 5;
-    T *vals = reinterpret_cast<T *>(sm_raw);
+    T *vals = reinterpret_cast<T *>(sm_raw + (WROWS ? (size_t)(threadIdx.x >> 5) * table_bytes : 0));
     int *keys = reinterpret_cast<int *>(vals + S);
     int *start = keys + S;      // [NB + 1] bucket counts -> bucket begins -> bucket ends
     int *misc = start + NB + 1; // [0] entries claimed so far
     int *bkey = misc + 3;       // keys in bucket order
     unsigned short *list = reinterpret_cast<unsigned short *>(bkey + nmax);
     unsigned short *idx = list + nmax; // slots in bucket order
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = lane_id(), nwarp = nthr >> 5;
-    const bool solo = nthr == 32; // one warp: claimed slots are written, not added to
+    const int lane = lane_id();
+    const int tid = WROWS ? lane : (int)threadIdx.x, nthr = WROWS ? 32 : (int)blockDim.x;
+    const int warp = WROWS ? 0 : tid >> 5, nwarp = nthr >> 5;
+    const bool solo = nthr == 32; // one warp per row: claimed slots are written, not added to
+    const int row0 = WROWS ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+    const int rstep = WROWS ? gridDim.x * (blockDim.x >> 5) : gridDim.x;
+    auto bar = [&]() {
+        if (WROWS)
+            __syncwarp();
+        else
+            __syncthreads();
+    };
     for (int i = tid; i < S; i += nthr)
     {
         keys[i] = -1;
         vals[i] = T(0);
     }
-    for (int r = blockIdx.x; r < nrows; r += gridDim.x)
+    for (int r = row0; r < nrows; r += rstep)
     {
         const int row = rows[r];
         const int out = __ldg(&Cp[row]);
@@ -1160,7 +1173,7 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
             start[b] = 0;
         if (tid == 0)
             misc[0] = 0;
-        __syncthreads();
+        bar();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         walk_flat_post<32, T, T>(
             kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv,
@@ -1221,7 +1234,7 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                     }
                 }
             });
-        __syncthreads();
+        bar();
         // bucket counts -> bucket begins (see bucket_sort_emit_warp for the idea of the sort)
         int carry = 0, mx = 0;
         for (int b0 = 0; b0 < NB; b0 += nthr)
@@ -1249,7 +1262,14 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                 start[b] = carry + ex;
             carry += tot;
         }
-        const bool clustered = __syncthreads_or(mx > kBucketMax);
+        bool clustered;
+        if (WROWS)
+        {
+            __syncwarp();
+            clustered = __any_sync(kFull, mx > kBucketMax);
+        }
+        else
+            clustered = __syncthreads_or(mx > kBucketMax);
         if (!clustered)
         {
             for (int i = tid; i < n; i += nthr)
@@ -1260,7 +1280,7 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                 idx[pos] = sl;
                 bkey[pos] = k;
             }
-            __syncthreads();
+            bar();
             for (int p = tid; p < n; p += nthr)
             {
                 const int sl = idx[p];
@@ -1296,7 +1316,7 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
                     rv[j] = vals[sl];
                 }
             }
-            __syncthreads();
+            bar();
             int P = 2;
             while (P < n)
                 P <<= 1;
@@ -1312,21 +1332,21 @@ __global__ void k_num_hash_list(const int *__restrict__ rows, int nrows, const i
             }
             for (int i = n + tid; i < P; i += nthr)
                 keys[i] = INT_MAX;
-            __syncthreads();
-            bitonic_sort_kv(keys, vals, P, tid, nthr, [&]() { __syncthreads(); });
+            bar();
+            bitonic_sort_kv(keys, vals, P, tid, nthr, bar);
             for (int i = tid; i < n; i += nthr)
             {
                 Cc[out + i] = keys[i];
                 Cv[out + i] = vals[i];
             }
-            __syncthreads();
+            bar();
             for (int i = tid; i < S; i += nthr) // full clear: slots outside [0, P) may still be set
             {
                 keys[i] = -1;
                 vals[i] = T(0);
             }
         }
-        __syncthreads();
+        bar();
     }
 }
 
