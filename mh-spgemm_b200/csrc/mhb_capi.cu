@@ -491,8 +491,10 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 31) / slice));
         CU(h->pool.ensure(slice * nblk));
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, 0, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
-               Cv, 0, h->pool.as<unsigned char>(), slots, scal);
+        // shared memory only for the sort of the compacted keys (6 B per entry + buckets)
+        const int sort_smem = (int)std::min<long long>(MHB_SMEM_MAX - 1024, 7LL * h->max_rownnz + 1024);
+        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, sort_smem, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow,
+                  Cp, Cc, Cv, 0, h->pool.as<unsigned char>(), slots, scal, sort_smem);
     }
     if ((n = n_of(NB_H_BLOCK_L)) > 0)
     {
@@ -671,8 +673,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_block<float>, MHB_SMEM_MAX - 256));
     CU(allow_smem(k_num_hash_group<32, double>, 8 * NB_H_WARP_L_SLOTS * 12));
     CU(allow_smem(k_num_hash_group<32, float>, 8 * NB_H_WARP_L_SLOTS * 8));
-    CU(allow_smem(k_num_hash_block<double>, NB_H_BLOCK_L_SLOTS * 12));
-    CU(allow_smem(k_num_hash_block<float>, NB_H_BLOCK_L_SLOTS * 8));
+    CU(allow_smem(k_num_hash_block<double>, MHB_SMEM_MAX - 1024));
+    CU(allow_smem(k_num_hash_block<float>, MHB_SMEM_MAX - 1024));
     return MHB_OK;
 }
 
