@@ -374,10 +374,10 @@ def main():
                          else "numeric (all bins)", "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4),
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from
-                         # one `ncu --set full` capture (profiles/r1f_numcompact_final.md); other workloads: null
-                         "traffic": 243588608 if (args.workload == "F" and world == 1) else None,
-                         "bound_on_chip": "latency at 13 warps/SM; LSU data pipe 52 %, issue 50 % "
-                                          "(profiles/r1f_numcompact_final.md)",
+                         # one `ncu --set full` capture (profiles/r1h_numcompact_final.md); other workloads: null
+                         "traffic": 243513856 if (args.workload == "F" and world == 1) else None,
+                         "bound_on_chip": "LSU data pipe 75 % (shared-memory accumulator traffic), issue 40 %, "
+                                          "14 warps/SM (profiles/r1h_numcompact_final.md)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ba_rank,
                          "kernel_ms": round(kern_ms, 4),
                          "pipeline_frac": round(ba / (ms * 1e-3) / 1e9 / peak / world, 4)},
