@@ -121,6 +121,8 @@ struct mhb_context
     int compact_rows = 1;                // option "compact_rows": use NB_WIN_COMPACT
     int claim_list = 1;                  // option "claim_list": k_num_hash_list for the 1 024 / 4 096-slot bins
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
+    int sym_twins = 1;                   // option "sym_twins": symbolic computes one row per run of twin rows of A
+    bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
     std::string err;
     // options
@@ -371,6 +373,11 @@ int launch_symbolic_bins(mhb_context *h)
     const int cap_blocks = h->num_sms * 16;
     int n;
     cudaStream_t st;
+    // twin flags of A's rows are known at this point only when A is B (family 1 computed them)
+    const unsigned char *a_twins = nullptr;
+    if (h->sym_twins)
+        a_twins = (h->Ap == h->Bp && h->Ac == h->Bc) ? h->bsame.as<unsigned char>()
+                                                     : (h->asame_early ? h->asame_buf.as<unsigned char>() : nullptr);
     h->have_bm_store = false;
     int frc = fork_bins(h);
     if (frc)
@@ -421,9 +428,9 @@ int launch_symbolic_bins(mhb_context *h)
     {
         constexpr int G = 32, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, 3 * GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>(), (unsigned *)nullptr, (int *)nullptr);
+               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>(), (unsigned *)nullptr, (int *)nullptr, a_twins);
     }
     if ((n = n_of(SB_H_G8)) > 0)
     {
@@ -445,10 +452,10 @@ int launch_symbolic_bins(mhb_context *h)
             CU(h->bm_slot.ensure(((size_t)h->M + 1) * 4));
         }
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+        LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, 3 * GPB), cap_blocks), kSymThreads,
                GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                SB_BM_G8_WORDS, h->bsame.as<unsigned char>(), h->have_bm_store ? h->bm_store.as<unsigned>() : nullptr,
-               h->have_bm_store ? h->bm_slot.as<int>() : nullptr);
+               h->have_bm_store ? h->bm_slot.as<int>() : nullptr, a_twins);
     }
     if ((n = n_of(SB_TINY)) > 0)
     {
@@ -713,6 +720,24 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     int *hs = h->h_scal.as<int>();
     CU(cudaMemsetAsync(scal, 0, SC_COUNT * 4, h->stream));
     CU(cudaEventRecord(h->ev[EV_ALLOC], h->stream));
+    // twin rows of A (same column list as the previous row): B's flags when A is B; otherwise
+    // compared now on a helper stream, hidden behind the mask build that only needs B
+    h->asame_early = false;
+    if (!(Ap == Bp && Ac == Bc) && h->sym_twins && M > 0)
+    {
+        CU(h->asame_buf.ensure((size_t)M + 1));
+        cudaStream_t side = h->serial ? h->stream : h->aux[0];
+        if (!h->serial)
+        {
+            CU(cudaEventRecord(h->ev_fork, h->stream));
+            CU(cudaStreamWaitEvent(side, h->ev_fork, 0));
+        }
+        LAUNCH_ON(h, side, k_rows_same_cols, cdiv((long long)M * 8, 256), 256, 0, M, Ap, Ac,
+                  h->asame_buf.as<unsigned char>());
+        if (!h->serial)
+            CU(cudaEventRecord(h->ev_join[0], side));
+        h->asame_early = true;
+    }
 
     // family 1: B mask matrix
     rc = build_mask_matrix(h, K, nnzB, Bp, Bc);
@@ -747,6 +772,8 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     std::memcpy(h->stats.sym_bin_size, hs + SC_SYM_SIZE, sizeof(int) * MHB_MAX_BINS);
 
     // family 3: nnz per C row
+    if (h->asame_early && !h->serial)
+        CU(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
     rc = launch_symbolic_bins(h);
     if (rc)
         return rc;
@@ -796,7 +823,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
         CU(h->asame_buf.ensure((size_t)M + 1));
         const bool needed = (h->num_off[NB_WIN_COMPACT + 1] > h->num_off[NB_WIN_COMPACT]) ||
                             (h->row_twins && h->num_off[NB_WIN_WARP + 1] > h->num_off[NB_WIN_WARP]);
-        if (M > 0 && needed)
+        if (M > 0 && needed && !h->asame_early)
             LAUNCH(h, k_rows_same_cols, cdiv((long long)M * 8, 256), 256, 0, M, Ap, Ac,
                    h->asame_buf.as<unsigned char>());
         h->asame = h->asame_buf.as<unsigned char>();
@@ -1052,6 +1079,8 @@ extern "C"
             h->compact_rows = (int)value;
         else if (k == "row_twins")
             h->row_twins = (int)value;
+        else if (k == "sym_twins")
+            h->sym_twins = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")

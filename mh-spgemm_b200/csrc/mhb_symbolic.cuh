@@ -31,6 +31,12 @@ constexpr int kSymThreads = 256;
 // tiles of B row i are OR-ed in (L2 latency overlaps the shared-memory updates).  A B row
 // whose pattern equals the previous B row's (same[k]) and that directly follows it in A's
 // row contributes nothing new and is skipped.
+// Twin rows of A (asame[i]: row i has the column list of row i-1, multi-dof FEM) have the
+// same C pattern: only the first row of a run is computed, its count (and stored bitmap slot)
+// is copied to the rows that follow it in the bin list.  Work is handed out per warp in
+// windows of 3 * (32/G) list entries; the run leaders of a window are dealt to the groups by
+// ballot + find-nth-set-bit, so that the groups of a warp stay busy although two of every
+// three rows need no work.
 template <int G>
 __global__ void __launch_bounds__(kSymThreads)
     k_sym_bitmap_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
@@ -38,16 +44,33 @@ __global__ void __launch_bounds__(kSymThreads)
                        const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                        const int4 *__restrict__ arow, int *__restrict__ counts, int wcap,
                        const unsigned char *__restrict__ same, unsigned *__restrict__ bm_store,
-                       int *__restrict__ bm_slot)
+                       int *__restrict__ bm_slot, const unsigned char *__restrict__ asame)
 {
     extern __shared__ unsigned sm_u[];
-    constexpr int GPB = kSymThreads / G;
+    constexpr int NG = 32 / G, WIN = 3 * NG, WPB = kSymThreads / 32;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     unsigned *bm = sm_u + (size_t)g * wcap;
     const int gbase = lane_id() & ~(G - 1);
-    for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
+    const int gw = (lane_id() / G); // group inside the warp
+    for (long long r0 = (long long)(blockIdx.x * WPB + (threadIdx.x >> 5)) * WIN; r0 < nrows;
+         r0 += (long long)gridDim.x * WPB * WIN)
     {
+      // run leaders of this window (a row that repeats its predecessor in the list is skipped)
+      bool lead = false;
+      {
+          const long long ri = r0 + lane_id();
+          if (lane_id() < WIN && ri < nrows)
+          {
+              const int rw = __ldg(&rows[ri]);
+              lead = !(asame && ri > 0 && __ldg(&rows[ri - 1]) == rw - 1 && __ldg(&asame[rw]));
+          }
+      }
+      const unsigned leaders = __ballot_sync(kFull, lead);
+      const int nlead = __popc(leaders);
+      for (int li = gw; li < nlead; li += NG)
+      {
+        const int r = (int)r0 + (int)__fns(leaders, 0, li + 1);
         const int row = rows[r];
         const int4 info = arow[row];
         const int tbase = info.z >> MHB_TILE_SHIFT;
@@ -125,8 +148,19 @@ __global__ void __launch_bounds__(kSymThreads)
             counts[row] = c;
             if (bm_store)
                 bm_slot[row] = r;
+            if (asame) // the twins that follow in the list share the result
+                for (int f = 1; r + f < nrows; ++f)
+                {
+                    const int rf = __ldg(&rows[r + f]);
+                    if (rf != row + f || !__ldg(&asame[rf]))
+                        break;
+                    counts[rf] = c;
+                    if (bm_store)
+                        bm_slot[rf] = r;
+                }
         }
         __syncwarp(gm);
+      }
     }
 }
 

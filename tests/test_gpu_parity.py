@@ -398,7 +398,8 @@ def test_fuzz_random_shapes(tool, orc, seed):
         assert_matches(orc, C, Cp, Cc, Cv)
 
 
-@pytest.mark.parametrize("opts", [dict(compact_rows=0), dict(compact_rows=0, row_twins=1), dict(compact_rows=1)])
+@pytest.mark.parametrize("opts", [dict(compact_rows=0), dict(compact_rows=0, row_twins=1), dict(compact_rows=1),
+                                  dict(compact_rows=1, sym_twins=0), dict(compact_rows=0, sym_twins=0)])
 @pytest.mark.parametrize("alias", [True, False])
 def test_window_kernel_variants_on_twin_rows(orc, opts, alias):
     """Multi-dof FEM input (twin rows in A and B): the dense-window kernel with B-twin folding,
