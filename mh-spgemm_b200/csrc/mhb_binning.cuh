@@ -60,6 +60,7 @@ __device__ __forceinline__ long long block_reduce_sum(long long v, long long *sh
 template <class Load>
 __global__ void __launch_bounds__(kScanThreads) k_scan_blocksums(Load in, long long n, long long *blocksums)
 {
+    pdl_prologue();
     __shared__ long long sh[32];
     long long base = (long long)blockIdx.x * kScanTile;
     long long s = 0;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Load in, long long 
                                                              int nblocks, int *out, int write_total,
                                                              long long *total64)
 {
+    pdl_prologue();
     __shared__ long long sh[32];
     __shared__ int warp_tot[32];
     // offset of this block = sum of the preceding block sums
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
                                                       unsigned char *__restrict__ binid, int *__restrict__ counts,
                                                       int *__restrict__ scal, int force_path)
 {
+    pdl_prologue();
     constexpr int kLong = 32 * G; // rows longer than this are walked by the whole warp
     constexpr int GPW = 32 / G;   // rows per warp and step
     __shared__ long long sh_ip[8], sh_tf[8];
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
                                                       unsigned char *__restrict__ binid, int *__restrict__ scal,
                                                       int force_path, int force_sym, int compact_ok)
 {
+    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n = 0;
     if (i < M)
@@ -323,6 +327,7 @@ constexpr int kBinThreads = 1024;
 __global__ void __launch_bounds__(kBinThreads) k_bin_count(int M, const unsigned char *__restrict__ binid,
                                                            int *__restrict__ blockhist, int nblocks)
 {
+    pdl_prologue();
     __shared__ int hist[MHB_MAX_BINS + 1];
     if (threadIdx.x <= MHB_MAX_BINS)
         hist[threadIdx.x] = 0;
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(32 * MHB_MAX_BINS) k_bin_offsets(int *__restri
                                                                    int nbins, int *__restrict__ size_out,
                                                                    int *__restrict__ off_out)
 {
+    pdl_prologue();
     __shared__ int total[MHB_MAX_BINS], base[MHB_MAX_BINS + 1];
     const int b = threadIdx.x >> 5, lane = lane_id();
     int *h = blockhist + (size_t)b * nblocks;
@@ -390,6 +396,7 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(int M, const unsign
                                                              const int *__restrict__ blockhist, int nblocks,
                                                              int *__restrict__ bins)
 {
+    pdl_prologue();
     __shared__ int warpcnt[32][MHB_MAX_BINS + 1];
     for (int t = threadIdx.x; t < 32 * (MHB_MAX_BINS + 1); t += kBinThreads)
         (&warpcnt[0][0])[t] = 0;

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -122,6 +123,7 @@ struct mhb_context
     int claim_list = 1;                  // option "claim_list": k_num_hash_list for the 1 024 / 4 096-slot bins
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
     int sym_twins = 1;                   // option "sym_twins": symbolic computes one row per run of twin rows of A
+    int pdl = 1;                         // option "pdl": programmatic dependent launch of the main-stream chain
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
     std::string err;
@@ -170,12 +172,24 @@ int fail(mhb_context *h, int code, const std::string &msg)
                             std::to_string(__LINE__) + ")");                                             \
     } while (0)
 
+// Kernels of the main-stream chain (mask build, scans, metrics, binning): every one of them
+// starts with pdl_prologue(), so they are launched with programmatic stream serialization --
+// the launch latency of kernel i+1 hides behind kernel i (a dozen 3-25 us kernels per call).
 #define LAUNCH(h, kern, grid, block, smem, ...)                                                          \
     do                                                                                                   \
     {                                                                                                    \
-        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);                                     \
+        cudaLaunchConfig_t cfg__ = {};                                                                   \
+        cfg__.gridDim = dim3((unsigned)(grid));                                                          \
+        cfg__.blockDim = dim3((unsigned)(block));                                                        \
+        cfg__.dynamicSmemBytes = (size_t)(smem);                                                         \
+        cfg__.stream = (h)->stream;                                                                      \
+        cudaLaunchAttribute at__[1];                                                                     \
+        at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                 \
+        at__[0].val.programmaticStreamSerializationAllowed = (h)->pdl ? 1 : 0;                           \
+        cfg__.attrs = at__;                                                                              \
+        cfg__.numAttrs = 1;                                                                              \
         ++(h)->launches;                                                                                 \
-        CU(cudaGetLastError());                                                                          \
+        CU(cudaLaunchKernelEx(&cfg__, kern, __VA_ARGS__));                                               \
     } while (0)
 
 #define LAUNCH_ON(h, st, kern, grid, block, smem, ...)                                                  \
@@ -980,6 +994,8 @@ extern "C"
             return MHB_ERR_CUDA; // no CPU fallback: without a CUDA device the library refuses to run
         mhb_context *h = new mhb_context();
         h->device = device;
+        if (const char *e = std::getenv("MHB_PDL")) // A/B switch for measurements
+            h->pdl = std::atoi(e);
         auto bail = [&](int code) {
             delete h;
             return code;
@@ -1081,6 +1097,8 @@ extern "C"
             h->row_twins = (int)value;
         else if (k == "sym_twins")
             h->sym_twins = (int)value;
+        else if (k == "pdl")
+            h->pdl = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")

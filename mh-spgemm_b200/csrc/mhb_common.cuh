@@ -64,6 +64,16 @@ __device__ __forceinline__ int group_max(int v, unsigned gm)
 // (key*107) % prime and cumulative-square probing (inc/common.h:72, inc/numeric.cuh:233),
 // which reaches only ~67 % of the slots; multiplicative hashing with
 // linear probing over a power-of-two table is a full cycle and needs no integer modulo.
+// Programmatic dependent launch (the small kernels of the binning / mask chain): wait for the
+// previous kernel of the stream -- its memory is visible after this -- then let the next
+// kernel of the chain start scheduling its blocks while this one runs.  A kernel launched the
+// ordinary way passes straight through both instructions.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned hash_slot(unsigned key, int logS)
 {
     return (key * 2654435761u) >> (32 - logS);

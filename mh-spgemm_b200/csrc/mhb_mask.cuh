@@ -23,6 +23,7 @@ namespace mhb
 __global__ void __launch_bounds__(256) k_mask_flags(const int *__restrict__ Bc, long long nnz, long long nwords,
                                                     unsigned *__restrict__ flags)
 {
+    pdl_prologue();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nwords * 32; j += stride)
     {
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) k_mask_flags(const int *__restrict__ Bc, 
 __global__ void __launch_bounds__(256) k_mask_rowstarts(int K, const int *__restrict__ Bp,
                                                         unsigned *__restrict__ flags)
 {
+    pdl_prologue();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K)
         return;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) k_mask_tileptr(int K, long long nnz, cons
                                                       const long long *__restrict__ total64,
                                                       int *__restrict__ tileptr, int4 *__restrict__ binfo)
 {
+    pdl_prologue();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > K)
         return;
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(256) k_mask_fill(const int *__restrict__ Bc, l
                                                    const int *__restrict__ wordprefix,
                                                    int *__restrict__ tilecol, unsigned *__restrict__ tilemask)
 {
+    pdl_prologue();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = lane_id();
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nwords * 32; j += stride)
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(256) k_mask_same(int K, const int4 *__restrict
                                                    const unsigned *__restrict__ tilemask,
                                                    unsigned char *__restrict__ same)
 {
+    pdl_prologue();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K)
         return;
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(256) k_rows_same_cols(int M, const int *__rest
                                                         const int *__restrict__ col,
                                                         unsigned char *__restrict__ same)
 {
+    pdl_prologue();
     constexpr int G = 8;
     const int l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
