@@ -117,6 +117,7 @@ struct mhb_context
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
     int aux_used = 0;
     bool serial = false; // option "serial_bins": one stream, for per-kernel timing
+    bool phase_serial = false; // this phase runs on the main stream only (serial, or one populated bin)
     DevBuf bsame, asame_buf, bm_store, bm_slot;
     bool have_bm_store = false;          // symbolic kept the bitmaps of its SB_BM_G8 rows
     int compact_rows = 1;                // option "compact_rows": use NB_WIN_COMPACT
@@ -202,17 +203,23 @@ int fail(mhb_context *h, int code, const std::string &msg)
 
 // Fork / join of the per-bin kernels of one phase: bin kernels are independent (disjoint rows,
 // disjoint outputs), so they are spread over the main stream and kAux helper streams.
-int fork_bins(mhb_context *h)
+int fork_bins(mhb_context *h, const int *off, int nbins)
 {
     h->aux_used = 0;
-    if (h->serial)
+    // a phase with a single populated bin (FEM-like inputs) stays on the main stream: no
+    // event round trip to a helper stream and back
+    int populated = 0;
+    for (int b = 1; b < nbins; ++b) // bin 0 is the empty-row bin: no kernel
+        populated += off[b + 1] > off[b];
+    h->phase_serial = h->serial || populated <= 1;
+    if (h->phase_serial)
         return MHB_OK;
     CU(cudaEventRecord(h->ev_fork, h->stream));
     return MHB_OK;
 }
 int next_bin_stream(mhb_context *h, cudaStream_t *out)
 {
-    if (h->serial)
+    if (h->phase_serial)
     {
         *out = h->stream;
         return MHB_OK;
@@ -233,7 +240,7 @@ int next_bin_stream(mhb_context *h, cudaStream_t *out)
 }
 int join_bins(mhb_context *h)
 {
-    if (h->serial)
+    if (h->phase_serial)
         return MHB_OK;
     int n = std::min(h->aux_used, (int)mhb_context::kAux);
     for (int a = 0; a < n; ++a)
@@ -393,7 +400,7 @@ int launch_symbolic_bins(mhb_context *h)
         a_twins = (h->Ap == h->Bp && h->Ac == h->Bc) ? h->bsame.as<unsigned char>()
                                                      : (h->asame_early ? h->asame_buf.as<unsigned char>() : nullptr);
     h->have_bm_store = false;
-    int frc = fork_bins(h);
+    int frc = fork_bins(h, off, SB_COUNT);
     if (frc)
         return frc;
     // big-row bins first (see launch_numeric_bins)
@@ -500,7 +507,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     const int *Ap = h->Ap, *Ac = h->Ac, *Bp = h->Bp, *Bc = h->Bc, *Cp = h->Cp;
     int n;
     cudaStream_t st;
-    int frc = fork_bins(h);
+    int frc = fork_bins(h, off, NB_COUNT);
     if (frc)
         return frc;
     // launch order: bins with the fewest, largest rows first, so that their long-running
