@@ -65,7 +65,8 @@ int mhb_set_stream(mhb_handle_t h, void *cuda_stream);
 /* Tuning / test knobs: "force_sym_path", "force_num_path" (0 auto, 1 window/bitmap only
  * where it fits, 2 hash only), "serial_bins" (1: per-bin kernels on one stream),
  * "nnz_limit" (report MHB_ERR_OVERFLOW above this nnz(C); default INT_MAX), "verbose";
- * kernel selection: "compact_rows" (1), "claim_list" (1), "row_twins" (0), "sym_twins" (1). */
+ * kernel selection: "compact_rows" (1), "claim_list" (1), "row_twins" (0), "sym_twins" (1), "pdl" (1:
+ * programmatic dependent launch of the main-stream kernel chain; env MHB_PDL overrides at create). */
 int mhb_set_option(mhb_handle_t h, const char *key, long long value);
 
 /* ---- the symbolic-then-numeric contract (MH_spgemm, src/main.cu:12-72) ---- */
