@@ -68,6 +68,10 @@ def _worker(rank, world, port, q):
     Bl = CSR(B.M, B.N, bp.numpy(), bc.numpy(), bv.numpy())
     Cp, Cc, Cv = orc.spgemm(blk, Bl)
     off, total = D.slice_offsets(int(Cp[-1]), rank, world, torch.device("cpu"))
+    # the per-step variant with preallocated buffers must give the same placement
+    sizes = D.SliceSizes(rank, world, torch.device("cpu"))
+    assert sizes.gather(int(Cp[-1])).offsets() == (off, total)
+    assert sizes.gather(7 + rank).offsets() == (7 * rank + (rank * (rank - 1)) // 2, 7 * world + world * (world - 1) // 2)
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((Cp, Cc, Cv, off, total), gathered, dst=0)
     # second layout: B row-sharded like A, halo-aware range exchange (send/recv)
