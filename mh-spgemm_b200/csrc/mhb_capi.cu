@@ -510,6 +510,25 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     int frc = fork_bins(h, off, NB_COUNT);
     if (frc)
         return frc;
+    // k_num_hash_list over one bin.  threads = 0: four rows (warps) per 128-thread block, each warp
+    // with a table of its own; otherwise one block of `threads` threads per row.
+    auto launch_hash_list = [&](int bin, int slots, int threads, int grid_cap) -> int {
+        const int rows_in_bin = off[bin + 1] - off[bin];
+        const int table = (int)hash_list_smem<T>(slots);
+        if (threads == 0)
+        {
+            auto kern = k_num_hash_list<T, true>;
+            LAUNCH_ON(h, st, kern, std::min(cdiv(rows_in_bin, 4), grid_cap), 128, 4 * table, bins + off[bin], rows_in_bin,
+                      Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, table);
+        }
+        else
+        {
+            auto kern = k_num_hash_list<T, false>;
+            LAUNCH_ON(h, st, kern, std::min(rows_in_bin, grid_cap), threads, table, bins + off[bin], rows_in_bin, Ap, Ac,
+                      Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, 0);
+        }
+        return MHB_OK;
+    };
     // launch order: bins with the fewest, largest rows first, so that their long-running
     // blocks start at once and overlap the bulk bins instead of forming a tail
     if ((n = n_of(NB_H_GLOBAL)) > 0)
@@ -542,10 +561,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            { auto kern = k_num_hash_list<T, false>;
-            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks), 256, hash_list_smem<T>(NB_H_BLOCK_S_SLOTS),
-                      bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-                      log2_ceil(NB_H_BLOCK_S_SLOTS), scal, 0); }
+        {
+            if (int e_ = launch_hash_list(NB_H_BLOCK_S, NB_H_BLOCK_S_SLOTS, 256, cap_blocks)) return e_;
+        }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
@@ -563,10 +581,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         // 1 024-slot tables: two warps share one table (64 threads) so that ~28-36 warps stay resident
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            { auto kern = k_num_hash_list<T, false>;
-            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks * 4), 64, hash_list_smem<T>(NB_H_WARP_L_SLOTS),
-                      bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_L_SLOTS),
-                      scal, 0); }
+        {
+            if (int e_ = launch_hash_list(NB_H_WARP_L, NB_H_WARP_L_SLOTS, 64, cap_blocks * 4)) return e_;
+        }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
@@ -606,9 +623,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            { auto kern = k_num_hash_list<T, false>;
-            LAUNCH_ON(h, st, kern, std::min(n, cap_blocks * 8), 32, hash_list_smem<T>(NB_H_WARP_M_SLOTS),
-                      bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal, 0); }
+        {
+            if (int e_ = launch_hash_list(NB_H_WARP_M, NB_H_WARP_M_SLOTS, 32, cap_blocks * 8)) return e_;
+        }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -622,10 +639,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            { auto kern = k_num_hash_list<T, true>; // four rows (warps) per block
-            LAUNCH_ON(h, st, kern, std::min(cdiv(n, 4), cap_blocks * 2), 128, 4 * hash_list_smem<T>(NB_H_WARP_S_SLOTS),
-                      bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal,
-                      (int)hash_list_smem<T>(NB_H_WARP_S_SLOTS)); }
+        {
+            if (int e_ = launch_hash_list(NB_H_WARP_S, NB_H_WARP_S_SLOTS, 0, cap_blocks * 2)) return e_;
+        }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
@@ -639,10 +655,9 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         if (h->claim_list)
-            { auto kern = k_num_hash_list<T, true>; // four rows (warps) per block
-            LAUNCH_ON(h, st, kern, std::min(cdiv(n, 4), cap_blocks * 2), 128, 4 * hash_list_smem<T>(NB_H_WARP_XS_SLOTS),
-                      bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal,
-                      (int)hash_list_smem<T>(NB_H_WARP_XS_SLOTS)); }
+        {
+            if (int e_ = launch_hash_list(NB_H_WARP_XS, NB_H_WARP_XS_SLOTS, 0, cap_blocks * 2)) return e_;
+        }
         else
         {
             constexpr int G = 32, GPB = kNumGroupThreads / G;
