@@ -3,6 +3,7 @@ include/mhb_spgemm.h declares; without a GPU it refuses to run (no CPU fallback)
 import ctypes as C
 import os
 import re
+import subprocess
 
 import mh_spgemm_b200  # noqa: F401
 from mh_spgemm_b200 import api
@@ -54,3 +55,30 @@ def test_compat_header_mentions_reference_interface():
     s = open(p).read()
     for token in ("class CSR", "class Tool", "class Timing", "MH_spgemm", "d_ptr", "d_col", "d_val", "H2D", "D2H"):
         assert token in s
+
+
+def test_bin_ladders_are_consistent(tmp_path):
+    """csrc/mhb_config.h compiled on the host: every (span, nnz, products, forced path) lands in a
+    bin whose kernel can hold the row (hash fill <= 5/8 numeric, <= 3/4 symbolic; windows and
+    bitmaps within the shared memory their launch requests)."""
+    exe = tmp_path / "ladders"
+    src = os.path.join(ROOT, "tests", "cpp", "ladders.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", str(exe), src])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing in the shipped package (Python or CUDA sources)
+    may import, include or load it."""
+    pkg = os.path.join(ROOT, "mh-spgemm_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                continue
+            text = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+            for needle in ("import oracle", "from oracle", "liboracle", "libmhref", "oracle/"):
+                if needle in text:
+                    bad.append((f, needle))
+    assert not bad, bad
