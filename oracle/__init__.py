@@ -5,6 +5,8 @@ May be imported only by tests/, ``__graft_entry__.smoke()`` and bench.py's
 
 * :class:`Oracle`    -- host Gustavson restatement (gcc + OpenMP), see gustavson.c for the
   reference file:line each function follows.
+* :class:`CuSparse`  -- cusparseSpGEMM with a selectable algorithm (DEFAULT / ALG1 / ALG2 / ALG3;
+  oracle/cusparse_check.cu, own code); needs a GPU at call time.
 * :class:`Reference` -- the UNMODIFIED reference kernels rebuilt for sm_100
   (oracle/_ref/libmhref.so, built by ``make -C oracle ref`` where /root/reference exists);
   needs a GPU at call time.
@@ -20,6 +22,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "_build", "liboracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libmhref.so")
+CSK_SO = os.path.join(_HERE, "_build", "libcusparse_check.so")
 REF_TREE = "/root/reference"
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -31,7 +34,7 @@ _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
 def build(ref: bool = True) -> None:
     """Compile the C restatement, and the reference where its tree is present."""
-    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all", "cusparse"])
     if ref and os.path.isdir(REF_TREE):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref", "-j8"])
 
@@ -140,6 +143,47 @@ class Oracle:
         bad = f(M, _c(p1, np.int64), pad(k1, np.int32), pad(v1, dt), _c(p2, np.int64), pad(k2, np.int32),
                 pad(v2, dt), float(rtol), C.byref(first))
         return int(bad), int(first.value)
+
+
+class CuSparse:
+    """cusparseSpGEMM (generic API) as an independent oracle; ALG2 / ALG3 bound the work buffers
+    (SURVEY.md 8f row 3).  Columns inside a row are sorted here before they are returned."""
+
+    ALGS = {"default": 0, "alg1": 1, "alg2": 2, "alg3": 3}
+
+    def __init__(self):
+        if not os.path.exists(CSK_SO):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "cusparse"])
+        L = C.CDLL(CSK_SO)
+        L.csk_free.argtypes = [C.c_void_p]
+        L.csk_spgemm.restype = C.c_int
+        L.csk_spgemm.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p, C.c_int,
+                                 C.c_float, _i32p, C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_double)),
+                                 C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        self.L = L
+
+    def spgemm(self, A, B, alg="default", chunk_fraction=0.2):
+        """-> dict(ptr, col, val, nnz, ms) or raises MemoryError / RuntimeError."""
+        Cp = np.zeros(A.M + 1, np.int32)
+        cc = C.POINTER(C.c_int)()
+        cv = C.POINTER(C.c_double)()
+        nnz = C.c_longlong(0)
+        ms = C.c_double(0)
+        rc = self.L.csk_spgemm(A.M, A.N, B.N, A.ptr, A.col, _c(A.val, np.float64), B.ptr, B.col,
+                               _c(B.val, np.float64), self.ALGS[alg], float(chunk_fraction), Cp, C.byref(cc),
+                               C.byref(cv), C.byref(nnz), C.byref(ms))
+        if rc == -2:
+            raise MemoryError(f"cusparseSpGEMM {alg}: insufficient resources")
+        if rc != 0:
+            raise RuntimeError(f"cusparseSpGEMM {alg} failed")
+        n = int(nnz.value)
+        col = np.ctypeslib.as_array(cc, shape=(max(n, 1),))[:n].astype(np.int32, copy=True)
+        val = np.ctypeslib.as_array(cv, shape=(max(n, 1),))[:n].astype(np.float64, copy=True)
+        self.L.csk_free(C.cast(cc, C.c_void_p))
+        self.L.csk_free(C.cast(cv, C.c_void_p))
+        rows = np.repeat(np.arange(A.M, dtype=np.int64), np.diff(Cp))
+        order = np.lexsort((col, rows))
+        return dict(ptr=Cp, col=col[order], val=val[order], nnz=n, ms=float(ms.value))
 
 
 class Reference:

@@ -338,6 +338,25 @@ def test_cusparse_cross_check():
     assert "CUSPARSE-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
 
+@pytest.mark.parametrize("alg", ["default", "alg1", "alg2", "alg3"])
+def test_cusparse_algorithms_cross_check(alg):
+    """cuSPARSE SpGEMM through our own harness (oracle/cusparse_check.cu) with the memory-bounded
+    algorithms the reference never uses (ALG2 / ALG3 with a chunk fraction).
+    Runs in a subprocess: a cuSPARSE failure must not poison this process's CUDA context."""
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import mh_spgemm_b200\n"
+        "from mh_spgemm_b200 import api, generators as G; from oracle import CuSparse\n"
+        "A = G.rmat(13, 8000, 40000, seed=12); B = G.fem3d(4, 4, 10, 3, seed=2)\n"
+        "t = api.Tool(0); cs = CuSparse()\n"
+        "for X in (A, B):\n"
+        "    C = t.spgemm_host(X, X); R = cs.spgemm(X, X, alg=%r, chunk_fraction=0.3)\n"
+        "    assert R['nnz'] == C.nnz and np.array_equal(R['ptr'], C.ptr) and np.array_equal(R['col'], C.col)\n"
+        "    np.testing.assert_allclose(R['val'], C.val, rtol=1e-12, atol=0)\n"
+        "print('CUSPARSE-ALG-OK')\n" % (ROOT, alg))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CUSPARSE-ALG-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 def test_global_memory_fallbacks_wide_matrix(tool, orc):
     """Columns beyond the 1.8 M that a shared-memory bitmap covers and rows beyond the largest
     shared-memory tables: the symbolic tile hash and the numeric hash both run from the
