@@ -126,6 +126,18 @@ class ClockSampler:
                 "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
+def cpu_model() -> str:
+    """CPU model of the box the baseline ran on (SURVEY.md 8d asks for it beside the thread count)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(A: CSR, B: CSR, intprod: int, budget_s: float = 12.0) -> dict:
     """Host Gustavson (the oracle port) on the box's cores: a reported baseline, not the target."""
     from oracle import Oracle
@@ -140,7 +152,7 @@ def cpu_baseline(A: CSR, B: CSR, intprod: int, budget_s: float = 12.0) -> dict:
     t = float(np.median(ts))
     return {"value": round(2.0 * intprod / t / 1e9, 3), "unit": UNIT, "cores": o.threads, "kind": "port",
             "sample": f"whole workload x{len(ts)} (median), host Gustavson symbolic+numeric, OpenMP",
-            "ms_per_step": round(t * 1e3, 3)}
+            "ms_per_step": round(t * 1e3, 3), "cpu": cpu_model()}
 
 
 # ---------------------------------------------------------------------------------------
