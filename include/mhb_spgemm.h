@@ -54,6 +54,11 @@ typedef struct mhb_stats {
     int sym_bin_size[16];    /* rows per symbolic bin  */
     int num_bin_size[16];    /* rows per numeric bin   */
     int gpu_launches;        /* kernels launched by the last call */
+    /* option "count_probes": probes of the hash kernels that found their slot taken by another
+     * key -- the reference's HASH_CONFLICT counter (inc/common.h:18, inc/numeric.cuh:116-118,
+     * inc/Calculate_C_nnz.cuh:153); 0 when the option is off */
+    long long hash_probes;     /* numeric phase (column hash)  */
+    long long sym_hash_probes; /* symbolic phase (tile hash)   */
 } mhb_stats;
 
 /* ---- lifetime (replaces Tool::allocate / Tool::release, src/Tool.cu:4-69) ---- */
@@ -66,7 +71,8 @@ int mhb_set_stream(mhb_handle_t h, void *cuda_stream);
  * where it fits, 2 hash only), "serial_bins" (1: per-bin kernels on one stream),
  * "nnz_limit" (report MHB_ERR_OVERFLOW above this nnz(C); default INT_MAX), "verbose";
  * kernel selection: "compact_rows" (1), "claim_list" (1), "row_twins" (0), "sym_twins" (1), "pdl" (1:
- * programmatic dependent launch of the main-stream kernel chain; env MHB_PDL overrides at create). */
+ * programmatic dependent launch of the main-stream kernel chain; env MHB_PDL overrides at create);
+ * "count_probes" (0): count failed hash probes into mhb_stats.hash_probes / sym_hash_probes. */
 int mhb_set_option(mhb_handle_t h, const char *key, long long value);
 
 /* ---- the symbolic-then-numeric contract (MH_spgemm, src/main.cu:12-72) ---- */
@@ -119,6 +125,16 @@ int mhb_spgemm_host_f32(mhb_handle_t h, int M, int K, int N,
                         const int *hB_ptr, const int *hB_col, const float *hB_val,
                         const int **hC_ptr, const int **hC_col, const float **hC_val,
                         long long *nnzC);
+/* ---- device-side CSR transpose: T = A^T (N x M), canonical CSR (rows of T hold A's row
+ *      indices ascending).  Replaces matrix_transposition (src/utils.cpp:20-46), which the
+ *      reference runs on the host to form B for its AAT mode (src/main.cu:98-101, flag
+ *      inc/common.h:37).  dT_ptr has N+1 entries, dT_col / dT_val nnz entries, all caller-owned
+ *      device arrays.  Deterministic (stable radix sort by column, no atomic cursors). ---- */
+int mhb_transpose_f64(mhb_handle_t h, int M, int N, int nnz, const int *dA_ptr, const int *dA_col,
+                      const double *dA_val, int *dT_ptr, int *dT_col, double *dT_val);
+int mhb_transpose_f32(mhb_handle_t h, int M, int N, int nnz, const int *dA_ptr, const int *dA_col,
+                      const float *dA_val, int *dT_ptr, int *dT_col, float *dT_val);
+
 /* pinned host memory for callers that want zero-staging uploads */
 int mhb_host_alloc(void **hptr, size_t bytes);
 int mhb_host_free(void *hptr);

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "mhb_symbolic", "mhb_numeric_f64", "mhb_numeric_f32", "mhb_spgemm_f64", "mhb_spgemm_f32",
     "mhb_device_free", "mhb_device_alloc", "mhb_memcpy_h2d", "mhb_memcpy_d2h", "mhb_spgemm_host_f64", "mhb_spgemm_host_f32", "mhb_host_alloc", "mhb_host_free",
     "mhb_form_mask_matrix_B", "mhb_get_row_info", "mhb_get_bins", "mhb_get_timing", "mhb_get_stats",
+    "mhb_transpose_f64", "mhb_transpose_f32",
 ]
 
 
@@ -54,12 +55,13 @@ class Timing(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("intprod", C.c_longlong), ("tileflop", C.c_longlong), ("ntiles_B", C.c_longlong),
                 ("nnzC", C.c_longlong), ("sym_bin_size", C.c_int * 16), ("num_bin_size", C.c_int * 16),
-                ("gpu_launches", C.c_int)]
+                ("gpu_launches", C.c_int), ("hash_probes", C.c_longlong), ("sym_hash_probes", C.c_longlong)]
 
     def as_dict(self):
         return dict(intprod=self.intprod, tileflop=self.tileflop, ntiles_B=self.ntiles_B, nnzC=self.nnzC,
                     sym_bins=dict(zip(SYM_BINS, list(self.sym_bin_size))),
-                    num_bins=dict(zip(NUM_BINS, list(self.num_bin_size))), gpu_launches=self.gpu_launches)
+                    num_bins=dict(zip(NUM_BINS, list(self.num_bin_size))), gpu_launches=self.gpu_launches,
+                    hash_probes=self.hash_probes, sym_hash_probes=self.sym_hash_probes)
 
 
 def load_library() -> C.CDLL:
@@ -92,6 +94,8 @@ def load_library() -> C.CDLL:
     for n in ("mhb_spgemm_host_f64", "mhb_spgemm_host_f32"):
         getattr(L, n).argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp, vp,
                                   C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
+    for n in ("mhb_transpose_f64", "mhb_transpose_f32"):
+        getattr(L, n).argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp, vp]
     L.mhb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.mhb_host_free.argtypes = [vp]
     L.mhb_form_mask_matrix_B.argtypes = [vp, ip, ip, ip, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
@@ -204,6 +208,10 @@ class Tool:
         """C = A*B.  A, B: CSR or PinnedCSR (B=None or B is A -> C = A*A, uploaded once)."""
         B = A if B is None else B
         dt = np.dtype(A.val.dtype)
+        if A.N != B.M:
+            raise ValueError(f"inner dimensions differ: A is {A.M}x{A.N}, B is {B.M}x{B.N}")
+        if np.dtype(B.val.dtype) != dt or dt not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError(f"A and B must share one value type (float64 or float32), got {dt} and {B.val.dtype}")
         f = self.L.mhb_spgemm_host_f64 if dt == np.float64 else self.L.mhb_spgemm_host_f32
         cp, cc, cv, nnz = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_longlong()
         self._chk(f(self.h, A.M, A.N, B.N, _hp(A.ptr), _hp(A.col), _hp(A.val), _hp(B.ptr), _hp(B.col),
@@ -258,6 +266,27 @@ class Tool:
     def numeric_into(self, dA_val, dB_val, dC_col, dC_val):
         f = self.L.mhb_numeric_f64 if _itemsize(dA_val) == 8 else self.L.mhb_numeric_f32
         self._chk(f(self.h, dA_val.data_ptr(), dB_val.data_ptr(), dC_col.data_ptr(), dC_val.data_ptr()))
+
+    def transpose_device(self, M, N, dA_ptr, dA_col, dA_val):
+        """T = A^T on the device (mhb_transpose_*): -> (dT_ptr[N+1], dT_col[nnz], dT_val[nnz])."""
+        nnz = dA_col.numel()
+        dT_ptr = _alloc_like(dA_ptr, N + 1, np.int32)
+        dT_col = _alloc_like(dA_ptr, max(nnz, 1), np.int32)
+        dT_val = _alloc_like(dA_val, max(nnz, 1), None)
+        f = self.L.mhb_transpose_f64 if _itemsize(dA_val) == 8 else self.L.mhb_transpose_f32
+        self._chk(f(self.h, M, N, nnz, dA_ptr.data_ptr(), dA_col.data_ptr(), dA_val.data_ptr(),
+                    dT_ptr.data_ptr(), dT_col.data_ptr(), dT_val.data_ptr()))
+        return dT_ptr, dT_col, dT_val
+
+    def transpose(self, A: CSR) -> CSR:
+        """Host CSR in, host CSR out through the device transpose (matrix_transposition,
+        src/utils.cpp:20-46, as a library call)."""
+        dp, dc, dv = DeviceArray(A.ptr), DeviceArray(A.col), DeviceArray(A.val)
+        tp, tc, tv = self.transpose_device(A.M, A.N, dp, dc, dv)
+        T = CSR(A.N, A.M, tp.numpy(), tc.numpy()[:A.nnz], tv.numpy()[:A.nnz])
+        for d in (dp, dc, dv, tp, tc, tv):
+            d.free()
+        return T
 
     def mask_matrix_B(self, K, N, dB_ptr, dB_col):
         """Family 1 alone -> (tileptr[K+1], tilecol[nt], tilemask[nt]) as numpy arrays."""

@@ -21,6 +21,7 @@
 #include "mhb_mask.cuh"
 #include "mhb_numeric.cuh"
 #include "mhb_symbolic.cuh"
+#include "mhb_transpose.cuh"
 
 using namespace mhb;
 
@@ -125,6 +126,7 @@ struct mhb_context
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
     int sym_twins = 1;                   // option "sym_twins": symbolic computes one row per run of twin rows of A
     int pdl = 1;                         // option "pdl": programmatic dependent launch of the main-stream chain
+    int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
     std::string err;
@@ -145,6 +147,7 @@ struct mhb_context
     HostBuf h_scal;
     // host-API staging
     DevBuf sA_ptr, sA_col, sA_val, sB_ptr, sB_col, sB_val, sC_ptr, sC_col, sC_val;
+    DevBuf tr_key[2], tr_idx[2], tr_hist; // radix-sort scratch of mhb_transpose_*
     HostBuf hC_ptr, hC_col, hC_val;
     cudaEvent_t ev[EV_COUNT] = {nullptr};
     bool ev_sym_valid = false, ev_num_valid = false;
@@ -316,17 +319,17 @@ int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
     } reqs[] = {
         {&h->flags, (size_t)(nW + 1) * 4},
         {&h->wordprefix, (size_t)(nW + 2) * 4},
-        {&h->tileptr, (size_t)(K + 2) * 4},
-        {&h->tilecol, (size_t)(nnzB + 1) * 4},
-        {&h->tilemask, (size_t)(nnzB + 1) * 4},
-        {&h->binfo, (size_t)(K + 1) * 16},
-        {&h->bsame, (size_t)(K + 1)},
-        {&h->arow, (size_t)(M + 1) * 16},
-        {&h->binid, (size_t)(M + 1)},
-        {&h->bins_sym, (size_t)(M + 1) * 4},
-        {&h->bins_num, (size_t)(M + 1) * 4},
+        {&h->tileptr, ((size_t)K + 2) * 4},
+        {&h->tilecol, ((size_t)nnzB + 1) * 4},
+        {&h->tilemask, ((size_t)nnzB + 1) * 4},
+        {&h->binfo, ((size_t)K + 1) * 16},
+        {&h->bsame, ((size_t)K + 1)},
+        {&h->arow, ((size_t)M + 1) * 16},
+        {&h->binid, ((size_t)M + 1)},
+        {&h->bins_sym, ((size_t)M + 1) * 4},
+        {&h->bins_num, ((size_t)M + 1) * 4},
         {&h->blockhist, (size_t)MHB_MAX_BINS * (size_t)(cdiv(std::max(M, 1), kBinThreads) + 1) * 4},
-        {&h->scan_tmp, (size_t)(cdiv(std::max<long long>(std::max<long long>(nW, M + 1), 1), kScanTile) + 2) * 8},
+        {&h->scan_tmp, (size_t)(cdiv(std::max<long long>(std::max<long long>(nW, (long long)M + 1), 1), kScanTile) + 2) * 8},
         {&h->scal, (size_t)SC_COUNT * 4},
     };
     for (auto &r : reqs)
@@ -392,6 +395,8 @@ int launch_symbolic_bins(mhb_context *h)
     int *scal = h->scal.as<int>();
     int *counts = h->Cp;
     const int cap_blocks = h->num_sms * 16;
+    unsigned long long *probes =
+        h->count_probes ? reinterpret_cast<unsigned long long *>(scal + SC_SYM_PROBES_LO) : nullptr;
     int n;
     cudaStream_t st;
     // twin flags of A's rows are known at this point only when A is B (family 1 computed them)
@@ -414,14 +419,14 @@ int launch_symbolic_bins(mhb_context *h)
         CU(h->pool.ensure(slice * nblk));
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
-               arow, counts, 0, h->pool.as<int>(), slots, scal);
+               arow, counts, 0, h->pool.as<int>(), slots, scal, probes);
     }
     if ((n = n_of(SB_H_BLOCK_L)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
                bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal);
+               log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal, probes);
     }
     if ((n = n_of(SB_BM_BLOCK)) > 0)
     {
@@ -435,7 +440,7 @@ int launch_symbolic_bins(mhb_context *h)
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
                bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal);
+               log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal, probes);
     }
     if ((n = n_of(SB_H_WARP)) > 0)
     {
@@ -443,7 +448,7 @@ int launch_symbolic_bins(mhb_context *h)
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
-               log2_ceil(SB_H_WARP_SLOTS), scal);
+               log2_ceil(SB_H_WARP_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_WARP)) > 0)
     {
@@ -459,7 +464,7 @@ int launch_symbolic_bins(mhb_context *h)
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
                GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
-               log2_ceil(SB_H_G8_SLOTS), scal);
+               log2_ceil(SB_H_G8_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_G8)) > 0)
     {
@@ -504,6 +509,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     const int4 *arow = h->arow.as<int4>();
     int *scal = h->scal.as<int>();
     const int cap_blocks = h->num_sms * 16;
+    unsigned long long *probes = h->count_probes ? reinterpret_cast<unsigned long long *>(scal + SC_PROBES_LO) : nullptr;
     const int *Ap = h->Ap, *Ac = h->Ac, *Bp = h->Bp, *Bc = h->Bc, *Cp = h->Cp;
     int n;
     cudaStream_t st;
@@ -519,13 +525,13 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         {
             auto kern = k_num_hash_list<T, true>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(rows_in_bin, 4), grid_cap), 128, 4 * table, bins + off[bin], rows_in_bin,
-                      Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, table);
+                      Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, table, probes);
         }
         else
         {
             auto kern = k_num_hash_list<T, false>;
             LAUNCH_ON(h, st, kern, std::min(rows_in_bin, grid_cap), threads, table, bins + off[bin], rows_in_bin, Ap, Ac,
-                      Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, 0);
+                      Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, 0, probes);
         }
         return MHB_OK;
     };
@@ -541,14 +547,14 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         // shared memory only for the sort of the compacted keys (6 B per entry + buckets)
         const int sort_smem = (int)std::min<long long>(MHB_SMEM_MAX - 1024, 7LL * h->max_rownnz + 1024);
         LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, sort_smem, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow,
-                  Cp, Cc, Cv, 0, h->pool.as<unsigned char>(), slots, scal, sort_smem);
+                  Cp, Cc, Cv, 0, h->pool.as<unsigned char>(), slots, scal, sort_smem, probes);
     }
     if ((n = n_of(NB_H_BLOCK_L)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
                bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
-               (unsigned char *)nullptr, 0LL, scal);
+               (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_BLOCK_L)) > 0)
     {
@@ -567,7 +573,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-                      log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal);
+                      log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
     {
@@ -587,7 +593,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-                      log2_ceil(NB_H_WARP_L_SLOTS), (unsigned char *)nullptr, 0LL, scal);
+                      log2_ceil(NB_H_WARP_L_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_COMPACT)) > 0)
     {
@@ -632,7 +638,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                       GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-                      Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal);
+                      Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal, probes);
         }
     }
     if ((n = n_of(NB_H_WARP_S)) > 0)
@@ -648,7 +654,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                       GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-                      Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal);
+                      Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal, probes);
         }
     }
     if ((n = n_of(NB_H_WARP_XS)) > 0)
@@ -664,7 +670,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                       GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
-                      Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal);
+                      Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal, probes);
         }
     }
     if ((n = n_of(NB_WIN_G8)) > 0)
@@ -683,7 +689,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
                GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
-               log2_ceil(NB_H_G8_SLOTS), scal);
+               log2_ceil(NB_H_G8_SLOTS), scal, probes);
     }
     if ((n = n_of(NB_TINY)) > 0)
     {
@@ -838,6 +844,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     std::memcpy(h->stats.num_bin_size, hs + SC_NUM_SIZE, sizeof(int) * MHB_MAX_BINS);
     h->stats.nnzC = h->nnzC;
     h->stats.gpu_launches = h->launches;
+    std::memcpy(&h->stats.sym_hash_probes, hs + SC_SYM_PROBES_LO, 8);
     *nnzC_out = h->nnzC;
     h->ev_sym_valid = true;
     h->timing.mem_alloc = ev_ms(h, EV_START, EV_ALLOC);
@@ -879,6 +886,8 @@ int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sy
         return fail(h, MHB_ERR_ARG, "null value / output pointer");
     CU(cudaSetDevice(h->device));
     int before = h->launches;
+    if (h->count_probes)
+        CU(cudaMemsetAsync(h->scal.as<int>() + SC_PROBES_LO, 0, 8, h->stream));
     CU(cudaEventRecord(h->ev[EV_NUM0], h->stream));
     int rc = launch_numeric_bins<T>(h, Av, Bv, Cc, Cv);
     if (rc)
@@ -889,11 +898,12 @@ int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sy
     if (sync)
     {
         int *hs = h->h_scal.as<int>();
-        CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 6 * 4, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         rc = check_dev_error(h, hs);
         if (rc)
             return rc;
+        std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
         h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
         if (h->ev_sym_valid)
             h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
@@ -935,8 +945,12 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
 {
     if (!hAp || !hBp || !hCp || !hCc || !hCv || !nnzC)
         return fail(h, MHB_ERR_ARG, "null pointer");
+    if (M < 0 || K < 0 || N < 0)
+        return fail(h, MHB_ERR_ARG, "negative dimension");
     CU(cudaSetDevice(h->device));
     const int nnzA = hAp[M], nnzB = hBp[K];
+    if (nnzA < 0 || nnzB < 0 || (nnzA > 0 && (!hAc || !hAv)) || (nnzB > 0 && (!hBc || !hBv)))
+        return fail(h, MHB_ERR_ARG, "bad host CSR: negative nnz or null col / val array");
     const bool alias = (hAp == hBp && hAc == hBc && (const void *)hAv == (const void *)hBv && M == K);
     cudaStream_t st = h->stream;
     CU(h->sA_ptr.ensure(((size_t)M + 1) * 4));
@@ -966,33 +980,118 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
     if (!alias)
         CU(cudaMemcpyAsync(h->sB_val.p, hBv, (size_t)nnzB * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
     CU(cudaEventRecord(h->ev_vals, h->copy_stream));
+    // every error exit below drains copy_stream first: the value upload reads the CALLER's
+    // host arrays, which the caller may reuse the moment this function returns
+    auto drain = [&](int code) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(st);
+        return code;
+    };
+#define CUD(call)                                                                                        \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return drain(fail(h, e__ == cudaErrorMemoryAllocation ? MHB_ERR_NOMEM : MHB_ERR_CUDA,        \
+                              std::string(#call) + ": " + cudaGetErrorString(e__)));                     \
+    } while (0)
     int rc = do_symbolic(h, M, K, N, nnzA, h->sA_ptr.as<int>(), h->sA_col.as<int>(), nnzB, dBp, dBc,
                          h->sC_ptr.as<int>(), nnzC);
     if (rc)
-        return rc;
+        return drain(rc);
     size_t n = (size_t)std::max<long long>(*nnzC, 1);
-    CU(h->sC_col.ensure(n * 4));
-    CU(h->sC_val.ensure(n * sizeof(T)));
-    CU(h->hC_col.ensure(n * 4));
-    CU(h->hC_val.ensure(n * sizeof(T)));
-    CU(cudaMemcpyAsync(h->hC_ptr.p, h->sC_ptr.p, ((size_t)M + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamWaitEvent(st, h->ev_vals, 0));
+    CUD(h->sC_col.ensure(n * 4));
+    CUD(h->sC_val.ensure(n * sizeof(T)));
+    CUD(h->hC_col.ensure(n * 4));
+    CUD(h->hC_val.ensure(n * sizeof(T)));
+    CUD(cudaMemcpyAsync(h->hC_ptr.p, h->sC_ptr.p, ((size_t)M + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
     rc = do_numeric<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false);
     if (rc)
-        return rc;
-    CU(cudaMemcpyAsync(h->hC_col.p, h->sC_col.p, (size_t)*nnzC * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->hC_val.p, h->sC_val.p, (size_t)*nnzC * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return drain(rc);
+    CUD(cudaMemcpyAsync(h->hC_col.p, h->sC_col.p, (size_t)*nnzC * 4, cudaMemcpyDeviceToHost, st));
+    CUD(cudaMemcpyAsync(h->hC_val.p, h->sC_val.p, (size_t)*nnzC * sizeof(T), cudaMemcpyDeviceToHost, st));
     int *hs = h->h_scal.as<int>();
-    CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CUD(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 6 * 4, cudaMemcpyDeviceToHost, st));
+    CUD(cudaStreamSynchronize(st));
+#undef CUD
     rc = check_dev_error(h, hs);
     if (rc)
         return rc;
+    std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
     h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
     h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
     *hCp = h->hC_ptr.as<int>();
     *hCc = h->hC_col.as<int>();
     *hCv = h->hC_val.as<T>();
+    return MHB_OK;
+}
+
+// ---- device-side CSR transpose (the AAT mode's B operand; src/utils.cpp:20-46) -------------
+template <typename T>
+int do_transpose(mhb_context *h, int M, int N, int nnz, const int *Ap, const int *Ac, const T *Av, int *Tp, int *Tc,
+                 T *Tv)
+{
+    if (M < 0 || N < 0 || nnz < 0)
+        return fail(h, MHB_ERR_ARG, "negative dimension");
+    if (!Ap || !Tp || (nnz > 0 && (!Ac || !Av || !Tc || !Tv)))
+        return fail(h, MHB_ERR_ARG, "null CSR pointer");
+    CU(cudaSetDevice(h->device));
+    h->launches = 0;
+    h->have_pattern = false; // scan_tmp / scal are shared with the SpGEMM phases
+    const int nblocks = cdiv(std::max(nnz, 1), kRadixTile);
+    const long long nhist = (long long)kRadixBins * nblocks;
+    CU(h->scan_tmp.ensure((size_t)(cdiv(std::max<long long>(std::max<long long>(nhist, (long long)N + 1), 1), kScanTile) + 2) * 8));
+    CU(h->scal.ensure((size_t)SC_COUNT * 4));
+    CU(cudaMemsetAsync(Tp, 0, ((size_t)N + 1) * 4, h->stream));
+    if (nnz == 0)
+    {
+        CU(cudaStreamSynchronize(h->stream));
+        return MHB_OK;
+    }
+    // T.ptr: column histogram of A, scanned in place
+    LAUNCH(h, k_tr_count_cols, std::min(cdiv(nnz, 256), h->num_sms * 16), 256, 0, Ac, (long long)nnz, Tp);
+    int rc = run_scan(h, LoadInt{Tp}, N, Tp, 1, nullptr);
+    if (rc)
+        return rc;
+    // stable LSD radix sort of the nonzeros by column, 8 bits per pass
+    int bits = 1;
+    while (bits < 31 && (1LL << bits) < (long long)N)
+        ++bits;
+    const int passes = (bits + kRadixBits - 1) / kRadixBits;
+    CU(h->tr_hist.ensure((size_t)nhist * 4));
+    if (passes > 1)
+        for (int b = 0; b < 2; ++b)
+        {
+            CU(h->tr_key[b].ensure((size_t)nnz * 4));
+            CU(h->tr_idx[b].ensure((size_t)nnz * 4));
+        }
+    const int *kin = Ac, *iin = nullptr;
+    int *hist = h->tr_hist.as<int>();
+    for (int p = 0; p < passes; ++p)
+    {
+        const int shift = p * kRadixBits;
+        LAUNCH(h, k_radix_count, nblocks, kRadixThreads, 0, kin, (long long)nnz, shift, hist, nblocks);
+        rc = run_scan(h, LoadInt{hist}, nhist, hist, 0, nullptr);
+        if (rc)
+            return rc;
+        if (p == passes - 1)
+        {
+            auto kern = k_radix_scatter<T, true>;
+            LAUNCH(h, kern, nblocks, kRadixThreads, 0, kin, iin, (long long)nnz, shift, (const int *)hist, nblocks,
+                   (int *)nullptr, (int *)nullptr, Ap, M, Av, Tc, Tv);
+        }
+        else
+        {
+            int *kout = h->tr_key[p & 1].as<int>(), *iout = h->tr_idx[p & 1].as<int>();
+            auto kern = k_radix_scatter<T, false>;
+            LAUNCH(h, kern, nblocks, kRadixThreads, 0, kin, iin, (long long)nnz, shift, (const int *)hist, nblocks, kout,
+                   iout, Ap, M, Av, (int *)nullptr, (T *)nullptr);
+            kin = kout, iin = iout;
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.gpu_launches = h->launches;
     return MHB_OK;
 }
 
@@ -1064,7 +1163,7 @@ extern "C"
         for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
                           &h->binid, &h->bsame, &h->asame_buf, &h->bm_store, &h->bm_slot, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
                           &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
-                          &h->sC_col, &h->sC_val})
+                          &h->sC_col, &h->sC_val, &h->tr_key[0], &h->tr_key[1], &h->tr_idx[0], &h->tr_idx[1], &h->tr_hist})
             b->release();
         for (HostBuf *b : {&h->h_scal, &h->hC_ptr, &h->hC_col, &h->hC_val})
             b->release();
@@ -1121,6 +1220,8 @@ extern "C"
             h->sym_twins = (int)value;
         else if (k == "pdl")
             h->pdl = (int)value;
+        else if (k == "count_probes")
+            h->count_probes = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")
@@ -1204,6 +1305,21 @@ extern "C"
             return MHB_ERR_ARG;
         return do_spgemm_host<float>(h, M, K, N, hA_ptr, hA_col, hA_val, hB_ptr, hB_col, hB_val, hC_ptr, hC_col,
                                      hC_val, nnzC);
+    }
+
+    int mhb_transpose_f64(mhb_handle_t h, int M, int N, int nnz, const int *dA_ptr, const int *dA_col,
+                          const double *dA_val, int *dT_ptr, int *dT_col, double *dT_val)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_transpose<double>(h, M, N, nnz, dA_ptr, dA_col, dA_val, dT_ptr, dT_col, dT_val);
+    }
+    int mhb_transpose_f32(mhb_handle_t h, int M, int N, int nnz, const int *dA_ptr, const int *dA_col,
+                          const float *dA_val, int *dT_ptr, int *dT_col, float *dT_val)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_transpose<float>(h, M, N, nnz, dA_ptr, dA_col, dA_val, dT_ptr, dT_col, dT_val);
     }
 
     int mhb_host_alloc(void **hptr, size_t bytes)

@@ -11,6 +11,11 @@ namespace mhb
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// Twin tag of a B-row index held in a lane register: the SIGN bit, so that every row index of
+// the int32 contract (K up to INT_MAX) keeps all of its 31 value bits.
+constexpr int kTwinTag = (int)0x80000000u;
+constexpr int kTwinMask = 0x7fffffff;
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m;
@@ -118,11 +123,23 @@ enum Scalar
     SC_MAX_TILEFLOP = 8,
     SC_MAX_ROWNNZ = 9,
     SC_ERROR = 10,
+    SC_PROBES_LO = 12,     // unsigned long long at [12..13]: failed probes of the numeric hash kernels (option count_probes)
+    SC_SYM_PROBES_LO = 14, // unsigned long long at [14..15]: same for the symbolic tile hash
     SC_SYM_SIZE = 16,               // MHB_MAX_BINS ints
     SC_SYM_OFF = 32,                // MHB_MAX_BINS + 1 ints
     SC_NUM_SIZE = 64,               // MHB_MAX_BINS ints
     SC_NUM_OFF = 80,                // MHB_MAX_BINS + 1 ints
     SC_COUNT = 128
 };
+
+// Adds this thread's failed-probe count to the statistics counter (option "count_probes";
+// probes == nullptr when the option is off).  The reference's HASH_CONFLICT counter
+// (inc/common.h:18, inc/numeric.cuh:116-118) counts the same event: a probe that found the
+// slot taken by another key.
+__device__ __forceinline__ void flush_probes(unsigned long long *probes, int np)
+{
+    if (probes && np)
+        atomicAdd(probes, (unsigned long long)np);
+}
 
 } // namespace mhb

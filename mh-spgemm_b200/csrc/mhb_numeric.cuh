@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                     ms = __ldg(&Bp[mk]);
                     me = __ldg(&Bp[mk + 1]);
                     if (__ldg(&bsame[mk]))
-                        mk |= 0x40000000;
+                        mk |= kTwinTag;
                 }
             };
             meta(s + l, bs, be, kk, av0, av1, av2);
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                 stage_a[0 * SG + l] = av0;
                 stage_a[1 * SG + l] = av1;
                 stage_a[2 * SG + l] = av2;
-                const int kprev = __shfl_up_sync(kFull, kk & 0x3fffffff, 1);
-                const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
+                const int kprev = __shfl_up_sync(kFull, kk & kTwinMask, 1);
+                const bool fol = l > 0 && l < cnt && (kk & kTwinTag) && (kk & kTwinMask) == kprev + 1;
                 const unsigned fmask = __ballot_sync(kFull, fol);
                 __syncwarp();
                 int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0, ni = 0;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                     ms = __ldg(&Bp[mk]);
                     me = __ldg(&Bp[mk + 1]);
                     if (__ldg(&bsame[mk]))
-                        mk |= 0x40000000;
+                        mk |= kTwinTag;
                 }
             };
             meta(s + l, bs, be, kk, av0, av1, av2);
@@ -436,8 +436,8 @@ __global__ void __launch_bounds__(kRowTwinThreads)
                 stage_a[0 * SG + l] = av0;
                 stage_a[1 * SG + l] = av1;
                 stage_a[2 * SG + l] = av2;
-                const int kprev = __shfl_up_sync(kFull, kk & 0x3fffffff, 1);
-                const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
+                const int kprev = __shfl_up_sync(kFull, kk & kTwinMask, 1);
+                const bool fol = l > 0 && l < cnt && (kk & kTwinTag) && (kk & kTwinMask) == kprev + 1;
                 const unsigned fmask = __ballot_sync(kFull, fol);
                 __syncwarp();
                 // two register sets: while one B-row step is accumulated the loads of the next are in flight
@@ -691,7 +691,7 @@ __global__ void k_num_win_block(const int *__restrict__ rows, int nrows, const i
 // Hash accumulation
 // =========================================================================================
 // Find-or-claim the slot of `key`; returns the slot, or -1 if the table is full.
-__device__ __forceinline__ int key_slot(int *keys, int logS, int key)
+__device__ __forceinline__ int key_slot(int *keys, int logS, int key, int &np)
 {
     const unsigned S1 = (1u << logS) - 1u;
     unsigned h = hash_slot((unsigned)key, logS);
@@ -706,6 +706,7 @@ __device__ __forceinline__ int key_slot(int *keys, int logS, int key)
             if (old == -1 || old == key)
                 return (int)h;
         }
+        ++np; // slot taken by another key (the reference's HASH_CONFLICT event)
         h = (h + 1) & S1;
     }
     return -1;
@@ -900,10 +901,11 @@ __global__ void __launch_bounds__(kNumGroupThreads)
                      const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                      const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
                      const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
-                     int *__restrict__ scal)
+                     int *__restrict__ scal, unsigned long long *__restrict__ probes)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int GPB = kNumGroupThreads / G;
+    int np = 0;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     const int S = 1 << logS;
@@ -925,7 +927,7 @@ __global__ void __launch_bounds__(kNumGroupThreads)
         const int products = __ldg(&arow[row]).x;
         if ((long long)products * 2 >= (long long)(e - s) * G)
             walk_sequential<G, 2, T, T>(gm, l, s, e, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
-                const int h = key_slot(keys, logS, c);
+                const int h = key_slot(keys, logS, c, np);
                 if (h >= 0)
                     vals[h] = fma(a, v, vals[h]);
                 else
@@ -933,7 +935,7 @@ __global__ void __launch_bounds__(kNumGroupThreads)
             });
         else
             walk_flat<G, T, T>(gm, l, s, e, 0, 1, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
-                const int h = key_slot(keys, logS, c);
+                const int h = key_slot(keys, logS, c, np);
                 if (h >= 0)
                     atomicAdd(&vals[h], a * v);
                 else
@@ -1006,6 +1008,7 @@ __global__ void __launch_bounds__(kNumGroupThreads)
         }
         __syncwarp(gm);
     }
+    flush_probes(probes, np);
 }
 
 // Bucket-rank sort for a row whose table lives in the GLOBAL pool: the compacted keys are
@@ -1080,10 +1083,12 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
                                  const T *__restrict__ Bv, const int4 *__restrict__ arow,
                                  const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv,
                                  int logS_fixed, unsigned char *__restrict__ pool,
-                                 long long pool_slots, int *__restrict__ scal, int sort_smem = 0)
+                                 long long pool_slots, int *__restrict__ scal, int sort_smem,
+                                 unsigned long long *__restrict__ probes)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
+    int np = 0;
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x)
     {
@@ -1116,7 +1121,7 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
         __syncthreads();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         walk_flat<32, T, T>(kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv, [&](int c, T v, T a) {
-            const int h = key_slot(keys, logS, c);
+            const int h = key_slot(keys, logS, c, np);
             if (h >= 0)
                 atomicAdd(&vals[h], a * v);
             else
@@ -1176,6 +1181,7 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
         }
         __syncthreads();
     }
+    flush_probes(probes, np);
 }
 
 // ---- hash with a claim list: one block per row, table in shared memory ------------------
@@ -1202,8 +1208,9 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
                                 const int *__restrict__ Bp, const int *__restrict__ Bc,
                                 const T *__restrict__ Bv, const int4 *__restrict__ arow,
                                 const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
-                                int *__restrict__ scal, int table_bytes)
+                                int *__restrict__ scal, int table_bytes, unsigned long long *__restrict__ probes)
 {
+    int np = 0;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
     const int S = 1 << logS, NB = S >> 2, nmax = (S >> 3) * 5;
@@ -1263,7 +1270,10 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
                         claimed = (int)h;
                     need = need && old != -1 && old != c;
                     if (need)
+                    {
+                        ++np;
                         h = (h + 1) & S1;
+                    }
                 }
                 if (need) // S probes without a home: the row has more entries than symbolic promised
                     atomicMax(scal + SC_ERROR, (int)DEVERR_TABLE_FULL);
@@ -1418,6 +1428,7 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         }
         bar();
     }
+    flush_probes(probes, np);
 }
 
 // ---- tiny rows: one thread per row ------------------------------------------------------

@@ -169,7 +169,7 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
             ms = __ldg(&Bp[mk]);
             me = __ldg(&Bp[mk + 1]);
             if (__ldg(&same[mk]))
-                mk |= 0x40000000;
+                mk |= kTwinTag;
         }
     };
     meta(s + l, bs, be, kk, av);
@@ -181,8 +181,8 @@ __device__ __forceinline__ void walk_sequential_twins(unsigned gm, int l, int s,
         const int cnt = min(G, e - j0);
         stage[l] = pack_meta<T>(bs, be, av);
         // follower = repeats the pattern of the nonzero just before it (inside this chunk)
-        const int kprev = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
-        const bool fol = l > 0 && l < cnt && (kk & 0x40000000) && (kk & 0x3fffffff) == kprev + 1;
+        const int kprev = __shfl_up_sync(gm, kk & kTwinMask, 1, G);
+        const bool fol = l > 0 && l < cnt && (kk & kTwinTag) && (kk & kTwinMask) == kprev + 1;
         const unsigned fmask = (__ballot_sync(gm, fol) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
         __syncwarp(gm); // stage[] visible to the group
         int pc[kPre], nq = 0, nqe = 0, nsz = 1, nb1 = 0, nb2 = 0;

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kSymThreads)
                 ms = __ldg(&tileptr[mk]);
                 me = __ldg(&tileptr[mk + 1]);
                 if (__ldg(&same[mk]))
-                    mk |= 0x40000000; // twin of row mk-1
+                    mk |= kTwinTag; // twin of row mk-1
             }
         };
         load_meta(s + l, ts, te, kk);
@@ -97,12 +97,12 @@ __global__ void __launch_bounds__(kSymThreads)
         {
             load_meta(j0 + G + l, nts, nte, nkk);
             // drop rows that repeat the pattern of the nonzero just before them
-            int pk = __shfl_up_sync(gm, kk & 0x3fffffff, 1, G);
+            int pk = __shfl_up_sync(gm, kk & kTwinMask, 1, G);
             if (l == 0)
                 pk = prev_k;
-            if ((kk & 0x40000000) && (kk & 0x3fffffff) == pk + 1)
+            if ((kk & kTwinTag) && (kk & kTwinMask) == pk + 1)
                 te = ts;
-            prev_k = __shfl_sync(gm, kk & 0x3fffffff, G - 1, G);
+            prev_k = __shfl_sync(gm, kk & kTwinMask, G - 1, G);
             // visit only the nonzeros that still have tiles to contribute (twins were emptied)
             unsigned live = (__ballot_sync(gm, te > ts) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
             int pc = -1, nq = 0, nqe = 0;
@@ -255,7 +255,7 @@ __device__ __forceinline__ void tile_insert(int *keys, unsigned *masks, int logS
 // probe loop leaves when every lane has its slot, so the mask update runs once per step
 // instead of once per divergent exit path.  Must be called by ALL lanes of `gm`.
 __device__ __forceinline__ int tile_insert_lockstep(unsigned gm, int *keys, unsigned *masks, int logS, int tc,
-                                                    unsigned m, int *scal)
+                                                    unsigned m, int *scal, int &np)
 {
     const unsigned S1 = (1u << logS) - 1u;
     unsigned h = hash_slot((unsigned)tc, logS);
@@ -268,7 +268,10 @@ __device__ __forceinline__ int tile_insert_lockstep(unsigned gm, int *keys, unsi
             if (old == -1 || old == tc)
                 more = false;
             else
+            {
+                ++np;
                 h = (h + 1) & S1;
+            }
         }
     }
     if (more)
@@ -283,10 +286,12 @@ __global__ void __launch_bounds__(kSymThreads)
     k_sym_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const int *__restrict__ tileptr,
                      const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
-                     int *__restrict__ counts, int logS, int *__restrict__ scal)
+                     int *__restrict__ counts, int logS, int *__restrict__ scal,
+                     unsigned long long *__restrict__ probes)
 {
     extern __shared__ unsigned sm_u[];
     constexpr int GPB = kSymThreads / G;
+    int np = 0;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     const int S = 1 << logS;
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kSymThreads)
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         walk_flat_post<G, NoVal, unsigned>(
             gm, l, s, e, 0, 1, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
-            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(gm, keys, masks, logS, tc, m, scal); },
+            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(gm, keys, masks, logS, tc, m, scal, np); },
             [](int) {});
         __syncwarp(gm);
         int c = 0;
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(kSymThreads)
             counts[row] = c;
         __syncwarp(gm);
     }
+    flush_probes(probes, np);
 }
 
 // One block per row; table in shared memory (pool == nullptr) or in a per-block slice of
@@ -324,10 +330,12 @@ __global__ void __launch_bounds__(kSymThreads)
                      const int *__restrict__ Ac, const int *__restrict__ tileptr,
                      const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                      const int4 *__restrict__ arow, int *__restrict__ counts, int logS_fixed,
-                     int *__restrict__ pool, long long pool_slots, int *__restrict__ scal)
+                     int *__restrict__ pool, long long pool_slots, int *__restrict__ scal,
+                     unsigned long long *__restrict__ probes)
 {
     extern __shared__ unsigned sm_u[];
     __shared__ int red[32];
+    int np = 0;
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x)
     {
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(kSymThreads)
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         walk_flat_post<32, NoVal, unsigned>(
             kFull, lane, s, e, warp, nwarp, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
-            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(kFull, keys, masks, logS, tc, m, scal); },
+            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(kFull, keys, masks, logS, tc, m, scal, np); },
             [](int) {});
         __syncthreads();
         int c = 0;
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(kSymThreads)
             counts[row] = c;
         __syncthreads();
     }
+    flush_probes(probes, np);
 }
 
 // ---- tiny rows: one thread per row ------------------------------------------------------

@@ -70,7 +70,19 @@ class Oracle:
             f = getattr(L, name)
             f.restype = C.c_int64
             f.argtypes = [C.c_int, _i64p, _i32p, fp, _i64p, _i32p, fp, C.c_double, C.POINTER(C.c_int64)]
+        L.orc_transpose.restype = None
+        L.orc_transpose.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_void_p, C.c_int, _i32p, _i32p, C.c_void_p]
         self.L = L
+
+    def transpose(self, A):
+        """T = A^T as the reference's host transpose builds it (src/utils.cpp:20-46)."""
+        from mh_spgemm_b200.csr import CSR
+        Tp = np.zeros(A.N + 1, np.int32)
+        Tc = np.zeros(max(A.nnz, 1), np.int32)
+        Tv = np.zeros(max(A.nnz, 1), A.val.dtype)
+        self.L.orc_transpose(A.M, A.N, A.ptr, A.col, A.val.ctypes.data, A.val.dtype.itemsize, Tp, Tc,
+                             Tv.ctypes.data)
+        return CSR(A.N, A.M, Tp, Tc[:A.nnz], Tv[:A.nnz])
 
     @property
     def threads(self) -> int:
@@ -207,7 +219,19 @@ class Reference:
         L.mhref_cusparse.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p,
                                      C.c_int, C.c_int, _i32p, C.POINTER(ip), C.POINTER(dp),
                                      C.POINTER(C.c_int), dp, dp]
+        L.mhref_transpose.restype = C.c_int
+        L.mhref_transpose.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p]
         self.L = L
+
+    def transpose(self, A):
+        """The reference's own host transpose (src/utils.cpp:20-46); needs no GPU."""
+        from mh_spgemm_b200.csr import CSR
+        Tp = np.zeros(A.N + 1, np.int32)
+        Tc = np.zeros(max(A.nnz, 1), np.int32)
+        Tv = np.zeros(max(A.nnz, 1), np.float64)
+        rc = self.L.mhref_transpose(A.M, A.N, A.ptr, A.col, _c(A.val, np.float64), Tp, Tc, Tv)
+        assert rc == 0
+        return CSR(A.N, A.M, Tp, Tc[:A.nnz], Tv[:A.nnz])
 
     @staticmethod
     def available() -> bool:

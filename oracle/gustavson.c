@@ -388,3 +388,29 @@ int64_t orc_nnzC(int M, int K, int N, const int *Ap, const int *Ac, const int *B
 
 ORC_COMPARE(orc_compare_f64, double)
 ORC_COMPARE(orc_compare_f32, float)
+
+/* CSR transpose T = A^T (N x M): count per column, exclusive scan, then append every
+ * nonzero to its column's list while walking A in (row, column) order, so that each row of
+ * T holds A's row indices ascending.  Restates matrix_transposition (src/utils.cpp:20-46),
+ * the host step that forms B for the reference's AAT mode (src/main.cu:98-101).
+ * Tp has N+1 entries, Tc / Tv nnz entries.  `vsize` = bytes per value (8 or 4). */
+void orc_transpose(int M, int N, const int *Ap, const int *Ac, const void *Av, int vsize, int *Tp, int *Tc,
+                   void *Tv)
+{
+    int64_t nnz = Ap[M];
+    memset(Tp, 0, sizeof(int) * ((size_t)N + 1));
+    for (int64_t j = 0; j < nnz; ++j)
+        Tp[Ac[j] + 1]++;
+    for (int c = 0; c < N; ++c)
+        Tp[c + 1] += Tp[c];
+    int *cursor = (int *)malloc(sizeof(int) * ((size_t)N + 1));
+    memcpy(cursor, Tp, sizeof(int) * ((size_t)N + 1));
+    for (int r = 0; r < M; ++r)
+        for (int j = Ap[r]; j < Ap[r + 1]; ++j)
+        {
+            int pos = cursor[Ac[j]]++;
+            Tc[pos] = r;
+            memcpy((char *)Tv + (size_t)pos * vsize, (const char *)Av + (size_t)j * vsize, (size_t)vsize);
+        }
+    free(cursor);
+}

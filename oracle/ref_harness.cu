@@ -29,6 +29,7 @@
 void MH_spgemm(const CSR &A, CSR &B, CSR &C, Timing &Timing, Tool &tools);
 void cusparse_spgemm(CSR *a, CSR *b, CSR *c, double *time);
 void warm_gpu();
+void matrix_transposition(CSR const &A, CSR &B); // src/utils.cpp:20 (host code, no GPU needed)
 
 namespace
 {
@@ -63,6 +64,23 @@ extern "C"
 {
 
     void mhref_free(void *p) { std::free(p); }
+
+    // The reference's own host transpose (src/utils.cpp:20-46), the B operand of its AAT mode.
+    // Runs without a GPU.  Tp[N+1], Tc[nnz], Tv[nnz] are caller arrays.
+    int mhref_transpose(int M, int N, const int *Ap, const int *Ac, const double *Av, int *Tp, int *Tc, double *Tv)
+    {
+        // ~CSR calls cudaFree (src/CSR.cu:14-22), which throws on a box without a GPU: the two
+        // object shells are therefore heap-allocated and only their host arrays are released
+        CSR *A = new CSR, *T = new CSR;
+        fill_csr(*A, M, N, Ap, Ac, Av);
+        matrix_transposition(*A, *T);
+        std::memcpy(Tp, T->ptr, sizeof(int) * (size_t)(N + 1));
+        std::memcpy(Tc, T->col, sizeof(int) * (size_t)A->nnz);
+        std::memcpy(Tv, T->val, sizeof(double) * (size_t)A->nnz);
+        A->h_release_csr();
+        T->h_release_csr();
+        return 0;
+    }
 
     // One C = A*B through the reference.  Inputs are HOST CSR arrays.
     //   reps/warmup : timed / untimed repetitions of the device-resident call

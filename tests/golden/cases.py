@@ -30,3 +30,20 @@ LARGE = {
 REFERENCE_FAULTS = {
     "poisson_32": lambda: (G.poisson2d(32), None),
 }
+
+# Inputs of the transpose fixtures (the reference's host matrix_transposition, src/utils.cpp:20-46,
+# run in the build container by make_golden_transpose.py -- it needs no GPU).
+TRANSPOSE = {
+    "rect_300x200": lambda: G.uniform_random(300, 200, 2500, seed=3),
+    "rmat_s10": lambda: G.rmat(10, 1000, 4000, seed=32),
+    "wide_40x70000": lambda: G.uniform_random(40, 70000, 3000, seed=41),   # 3 radix passes, many empty columns
+    "tall_5000x9": lambda: G.uniform_random(5000, 9, 20000, seed=42),      # 1 radix pass, long T rows
+    "fem_3x3x6x2": lambda: G.fem3d(3, 3, 6, 2, seed=31),
+}
+
+# BASELINE configs[3]: the twelve suite analogs that fit a test run (the four large shapes --
+# wb-edu, cage15, GAP-road, delaunay_n24 -- are in SUITE_LARGE and run only with MHB_SLOW=1).
+SUITE12 = ["pdb1HYS", "pwtk", "webbase-1M", "cage12", "cant", "hood", "rma10", "scircuit", "shipsec1", "cop20k_A",
+           "mac_econ_fwd500", "offshore"]
+SUITE_LARGE = ["wb-edu", "cage15", "GAP-road", "delaunay_n24"]
+SUITE = {name: (lambda name=name: (G.suite(name), None)) for name in SUITE12 + SUITE_LARGE}

@@ -1,8 +1,10 @@
 """Generate the golden fixtures by running the UNMODIFIED reference kernels
 (oracle/_ref/libmhref.so, rebuilt for sm_100) on a B200:
 
-    gpurun -- python tests/golden/make_golden.py gpurun_out/golden
+    gpurun -- python tests/golden/make_golden.py gpurun_out/golden [--suite]
     cp gpurun_out/golden/* tests/golden/
+
+--suite records the twelve suite analogs of BASELINE configs[3] (ref_suite_<name>.json).
 
 Each case runs in its own process so a fault inside the reference cannot poison the rest.
 Small cases store the full CSR of C; large cases store nnz, SHA-256 of row_ptr and
@@ -33,7 +35,8 @@ def checksums(ptr, col, val):
 def run_case(name, outdir):
     from oracle import Reference
     table = {**cases.SMALL, **cases.LARGE, **cases.REFERENCE_FAULTS}
-    A, B = table[name]()
+    suite = name.startswith("suite_")
+    A, B = cases.SUITE[name[6:]]() if suite else table[name]()
     B = A if B is None else B
     R = Reference().spgemm(A, B, reps=1, warmup=0, e2e_reps=0, want_mask=True)
     tp, tc, tm = R["mask"]
@@ -54,17 +57,20 @@ def run_case(name, outdir):
 def main():
     outdir = sys.argv[1]
     os.makedirs(outdir, exist_ok=True)
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and sys.argv[2] != "--suite":
         return run_case(sys.argv[2], outdir)
     summary = {}
-    for name in [*cases.SMALL, *cases.LARGE, *cases.REFERENCE_FAULTS]:
+    names = [*cases.SMALL, *cases.LARGE, *cases.REFERENCE_FAULTS]
+    if len(sys.argv) > 2:  # --suite: only the twelve suite analogs of BASELINE configs[3]
+        names = ["suite_" + n for n in cases.SUITE12]
+    for name in names:
         p = subprocess.run([sys.executable, os.path.abspath(__file__), outdir, name], capture_output=True, text=True,
                            timeout=900)
         ok = p.returncode == 0 and os.path.exists(os.path.join(outdir, f"ref_{name}.json"))
         summary[name] = "ok" if ok else ("reference faulted: " + (p.stdout + p.stderr).strip().splitlines()[0][:200]
                                          if (p.stdout + p.stderr).strip() else "reference faulted")
         print(name, summary[name], flush=True)
-    with open(os.path.join(outdir, "ref_summary.json"), "w") as f:
+    with open(os.path.join(outdir, "ref_suite_summary.json" if len(sys.argv) > 2 else "ref_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
 
 

@@ -314,9 +314,26 @@ def test_cli_driver_matches_reference_report(tmp_path, orc):
     np.testing.assert_allclose(C.val, Cv, rtol=1e-12)
     p = run(str(pa))
     assert "C=AA must have rowA = colA. Exit." in p.stdout
-    p = run(str(pa), "--aat")
-    Tp, _, _ = orc.spgemm(A, A.transpose())
-    assert p.returncode == 0 and f"C.nnz = {Tp[-1]}" in p.stdout
+    # AAT: B = A^T through the device transpose; the WHOLE product is compared, not its size
+    p = run(str(pa), "--aat", "--out", str(tmp_path / "aat.mtx"), "--write", str(tmp_path / "data"))
+    Tp, Tc, Tv = orc.spgemm(A, orc.transpose(A))
+    assert p.returncode == 0 and f"C.nnz = {Tp[-1]}" in p.stdout, p.stdout + p.stderr
+    C, _ = read_mtx(str(tmp_path / "aat.mtx"))
+    assert C.M == A.M and C.N == A.M
+    assert np.array_equal(C.ptr, Tp) and np.array_equal(C.col, Tc)
+    np.testing.assert_allclose(C.val, Tv, rtol=1e-12)
+    # WRITE (src/main.cu:201-213): one "%.2f" Gflops line appended per run
+    lines = open(tmp_path / "data" / "Gflops_MH-SpGEMM.csv").read().split()
+    assert len(lines) == 1 and float(lines[0]) > 0
+    # process.sh: a list of names resolved under a root directory, missing files skipped with a warning
+    os.makedirs(tmp_path / "matrix" / "fem")
+    os.replace(ps, tmp_path / "matrix" / "fem" / "fem.mtx")
+    (tmp_path / "list.txt").write_text("fem\nnot_there\n")
+    p = run("--list", str(tmp_path / "list.txt"), "--root", str(tmp_path / "matrix"), "--write", str(tmp_path / "data"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Total matrices to process: 2" in p.stdout and "Warning: File not found" in p.stdout
+    assert "All listed matrices processed successfully." in p.stdout
+    assert len(open(tmp_path / "data" / "Gflops_MH-SpGEMM.csv").read().split()) == 2
 
 
 def test_cusparse_cross_check():
@@ -443,3 +460,121 @@ def test_window_kernel_variants_on_twin_rows(orc, opts, alias):
     Cp2, Cc2, Cv2 = orc.spgemm(A2, B)
     assert_matches(orc, C2, Cp2, Cc2, Cv2)
     t.release()
+
+
+@pytest.mark.parametrize("name", list(cases.TRANSPOSE))
+def test_device_transpose_matches_reference(tool, orc, name):
+    """mhb_transpose_* (stable radix sort by column) against the vectors recorded from the
+    reference's host transpose, bit-for-bit including the values; fp32 too."""
+    A = cases.TRANSPOSE[name]()
+    ref = np.load(os.path.join(GOLD, f"ref_transpose_{name}.npz"))
+    T = tool.transpose(A)
+    assert (T.M, T.N) == (A.N, A.M)
+    assert np.array_equal(T.ptr, ref["ptr"]) and np.array_equal(T.col, ref["col"]) and np.array_equal(T.val, ref["val"])
+    assert tool.stats["gpu_launches"] > 0
+    T32 = tool.transpose(A.astype(np.float32))
+    assert T32.val.dtype == np.float32 and np.array_equal(T32.col, ref["col"])
+    assert np.array_equal(T32.val, ref["val"].astype(np.float32))
+
+
+def test_device_transpose_edges_and_involution(tool, orc):
+    """Empty matrix, empty rows / columns, one long column (a hub), and (A^T)^T == A on a
+    skewed 260 K-nonzero input (4096-item radix tiles: many blocks, three passes)."""
+    E = CSR(4, 6, np.zeros(5, np.int32), [], [])
+    T = tool.transpose(E)
+    assert (T.M, T.N, T.nnz) == (6, 4, 0) and np.array_equal(T.ptr, np.zeros(7, np.int32))
+    A = G.with_dense_rows(G.rmat(17, 120_000, 260_000, seed=44), 3, 30_000, seed=45)
+    T = tool.transpose(A)
+    O = orc.transpose(A)
+    assert np.array_equal(T.ptr, O.ptr) and np.array_equal(T.col, O.col) and np.array_equal(T.val, O.val)
+    TT = tool.transpose(T)
+    assert np.array_equal(TT.ptr, A.ptr) and np.array_equal(TT.col, A.col) and np.array_equal(TT.val, A.val)
+
+
+@pytest.mark.parametrize("name", ["rect_300x200", "wide_40x70000", "fem_3x3x6x2"])
+def test_aat_product_full(tool, orc, name):
+    """The reference's second standard workload, C = A * A^T (AAT, inc/common.h:37): device
+    transpose feeding the SpGEMM, structure bit-exact and values to 1e-12 against the oracle;
+    C is symmetric in structure."""
+    A = cases.TRANSPOSE[name]()
+    C = tool.spgemm_host(A, tool.transpose(A))
+    Cp, Cc, Cv = orc.spgemm(A, orc.transpose(A))
+    assert_matches(orc, C, Cp, Cc, Cv)
+    P = C.to_scipy()
+    P.data[:] = 1
+    assert (P != P.T).nnz == 0
+
+
+def test_hash_probe_counter(orc):
+    """Option count_probes == the reference's HASH_CONFLICT statistic (inc/common.h:18): zero
+    when off, zero for a dense-path input, positive for hashed rows, and the product is
+    unchanged by counting."""
+    t = api.Tool(0)
+    A = G.rmat(14, 16000, 60000, seed=6)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    C0 = t.spgemm_host(A, A)
+    assert t.stats["hash_probes"] == 0 and t.stats["sym_hash_probes"] == 0
+    t.set_option("count_probes", 1)
+    t.set_option("force_sym_path", 2)
+    t.set_option("force_num_path", 2)
+    C1 = t.spgemm_host(A, A)
+    st = t.stats
+    assert_matches(orc, C1, Cp, Cc, Cv)
+    assert np.array_equal(C0.col, C1.col)
+    assert st["hash_probes"] > 0 and st["sym_hash_probes"] > 0
+    assert st["hash_probes"] < 4 * st["intprod"]  # fill <= 5/8 with linear probing: a few probes per product
+    C2 = t.spgemm_host(A, A)  # the counter restarts with every call
+    assert t.stats["hash_probes"] == st["hash_probes"] or abs(t.stats["hash_probes"] - st["hash_probes"]) < st["hash_probes"]
+    t.set_option("force_sym_path", 1)
+    t.set_option("force_num_path", 1)
+    F = G.fem3d(4, 4, 10, 3, seed=5)
+    t.spgemm_host(F, F)
+    assert t.stats["hash_probes"] == 0 and t.stats["sym_hash_probes"] == 0
+    t.release()
+
+
+def test_shape_and_dtype_mismatch_are_rejected(tool):
+    A = G.uniform_random(50, 60, 300, seed=1)
+    B = G.uniform_random(50, 60, 300, seed=2)
+    with pytest.raises(ValueError):
+        tool.spgemm_host(A, B)  # A.N != B.M
+    with pytest.raises(TypeError):
+        tool.spgemm_host(A, A.transpose().astype(np.float32))
+
+
+@pytest.mark.parametrize("name", cases.SUITE12)
+def test_suite_analog_matches_reference(tool, name):
+    """BASELINE configs[3]: C = A*A on the synthetic analog of every 16matrix.txt shape that
+    fits a test run; row_ptr / col_idx must be bit-exact (SHA-256) with what the reference's
+    own kernels produced on a B200 for the same input (tests/golden/ref_suite_*.json, written
+    by make_golden.py), values by checksum, rows sorted and duplicate-free."""
+    meta = json.load(open(os.path.join(GOLD, f"ref_suite_{name}.json")))
+    A, _ = cases.SUITE[name]()
+    assert (A.M, A.nnz) == (meta["M"], meta["nnzA"])
+    C = tool.spgemm_host(A, A)
+    assert C.nnz == meta["nnz"]
+    assert sha(C.ptr, np.int32) == meta["sha_ptr"]
+    assert sha(C.col, np.int32) == meta["sha_col"]
+    assert float(C.val.sum()) == pytest.approx(meta["sum_val"], rel=1e-10)
+    w = (np.arange(C.val.size, dtype=np.int64) % 97 + 1).astype(np.float64)
+    assert float((C.val * w).sum()) == pytest.approx(meta["sum_weighted"], rel=1e-10)
+    assert C.is_canonical()
+
+
+@pytest.mark.parametrize("name", cases.SUITE_LARGE)
+def test_suite_large_analog(tool, name):
+    """The four large shapes (16-24 M rows / up to 1.75 G nnz(C)): minutes of host-side
+    generation and tens of GB of pinned memory, so opt-in (MHB_SLOW=1)."""
+    if os.environ.get("MHB_SLOW") != "1":
+        pytest.skip("set MHB_SLOW=1 to run the four large suite analogs")
+    A, _ = cases.SUITE[name]()
+    C = tool.spgemm_host(A, A, copy=False)
+    path = os.path.join(GOLD, f"ref_suite_{name}.json")
+    if os.path.exists(path):  # the reference faults on two of them (DESIGN.md section 4)
+        meta = json.load(open(path))
+        assert C.nnz == meta["nnz"] and sha(C.ptr, np.int32) == meta["sha_ptr"] and sha(C.col, np.int32) == meta["sha_col"]
+    S = A.to_scipy()
+    want = S @ (S @ np.ones(A.N))
+    got = np.add.reduceat(np.append(C.val, 0.0), np.minimum(C.ptr[:-1], C.nnz))
+    got[np.diff(C.ptr) == 0] = 0.0
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-9)

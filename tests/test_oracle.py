@@ -107,3 +107,20 @@ def test_empty_and_ragged(orc):
     A = CSR(3, 3, [0, 0, 3, 3], [0, 1, 2], [1.0, 2.0, 3.0])  # empty first and last rows
     Cp, Cc, Cv = orc.spgemm(A, A)
     assert Cp.tolist() == [0, 0, 3, 3] and Cc.tolist() == [0, 1, 2] and Cv.tolist() == [2.0, 4.0, 6.0]
+
+
+@pytest.mark.parametrize("name", list(cases.TRANSPOSE))
+def test_oracle_transpose_matches_reference(orc, name):
+    """The AAT mode's B operand: the oracle's transpose against vectors recorded from the
+    reference's own matrix_transposition (src/utils.cpp:20-46; make_golden_transpose.py)."""
+    A = cases.TRANSPOSE[name]()
+    ref = np.load(os.path.join(GOLD, f"ref_transpose_{name}.npz"))
+    T = orc.transpose(A)
+    assert T.M == A.N and T.N == A.M
+    assert np.array_equal(T.ptr, ref["ptr"]) and np.array_equal(T.col, ref["col"])
+    assert np.array_equal(T.val, ref["val"])  # values are moved, not computed: bit-for-bit
+    assert T.is_canonical()
+    N = A.transpose()  # the numpy transpose of the host container agrees too
+    assert np.array_equal(N.ptr, T.ptr) and np.array_equal(N.col, T.col) and np.array_equal(N.val, T.val)
+    T32 = orc.transpose(A.astype(np.float32))
+    assert T32.val.dtype == np.float32 and np.array_equal(T32.col, T.col)
