@@ -157,8 +157,81 @@ int mhb_get_row_info(mhb_handle_t h, const int **d_row_info /* int4 per row */);
 int mhb_get_bins(mhb_handle_t h, int which, int *nbins, const int **d_bins,
                  int *h_bin_offset /* 17 ints */);
 
+/* cudaStream_t the handle currently launches on (for callers that order their own work). */
+int mhb_get_stream(mhb_handle_t h, void **cuda_stream);
+
 int mhb_get_timing(mhb_handle_t h, mhb_timing *out);
 int mhb_get_stats(mhb_handle_t h, mhb_stats *out);
+
+/* =========================================================================================
+ * Row-sharded SpGEMM across the GPUs of one box -- one process (or thread) per GPU, one
+ * mhb_shard_t per rank on top of that rank's mhb_handle_t.
+ *
+ * The reference is single-GPU (no NCCL / MPI / peer access anywhere under src/ or inc/); this
+ * is the multi-GPU form of the same call, MH_spgemm (src/main.cu:12-72), for a C++ driver
+ * shaped like src/main.cu:74-217 that owns one row block per GPU:
+ *   A  rows [a0, a1) on this rank: local CSR (row_ptr rebased to 0), GLOBAL column ids in [0, K)
+ *   B  row-sharded by `bounds` (bounds[r] .. bounds[r+1] owned by rank r): local row_ptr
+ *      rebased to 0, GLOBAL column ids in [0, N)
+ *   C  every rank keeps its own CSR slice (local int32 row_ptr); the global matrix is the
+ *      concatenation, row_ptr shifted by the slice offsets (int64) of mhb_shard_offsets().
+ * Gustavson rows are independent, so the only exchange is B: a rank needs the rows of B that
+ * the columns of its A block reference.  They are read ONE-SIDEDLY over NVLink from windows
+ * the owners export with CUDA IPC (peer-mapped memory; no send/recv pairing, no host-side
+ * collective in a step): mhb_shard_exchange() = one flag store per peer ("my shard of B is
+ * final for this step") + one kernel that waits for its owners' flags and copies the missing
+ * pieces into this rank's contiguous image of B.  Slice sizes travel the same way.
+ *
+ * The library does not own a transport for the set-up: the caller moves fixed-size blobs
+ * between the ranks with whatever it has (MPI, torch.distributed, files, shared memory).
+ * Set-up sequence (every rank; the all-gathers are the caller's):
+ *   mhb_shard_create -> mhb_shard_set_A -> mhb_shard_export(1) -> [all-gather blobs]
+ *   -> mhb_shard_import(1) -> mhb_shard_export(2) -> [all-gather] -> mhb_shard_import(2)
+ *   -> mhb_shard_own_B: where this rank keeps its shard of B's col / val (inside its image).
+ * Per step: [write B's shard] -> mhb_shard_exchange -> mhb_shard_symbolic -> (allocate C)
+ *   -> mhb_shard_numeric_* -> mhb_shard_post_size; mhb_shard_offsets when C is assembled.
+ * A rank whose block holds more than 2^31-1 products cuts it into row slices
+ * [r_lo, r_hi) and calls symbolic / numeric once per slice after ONE exchange.
+ * ========================================================================================= */
+typedef struct mhb_shard *mhb_shard_t;
+#define MHB_SHARD_BLOB_BYTES 128
+
+int mhb_shard_create(mhb_shard_t *out, mhb_handle_t h, int rank, int world, int K, int N,
+                     int value_bytes /* 8 or 4 */, const long long *bounds /* world+1 row bounds of B */);
+int mhb_shard_destroy(mhb_shard_t s);
+const char *mhb_shard_last_error(mhb_shard_t s);
+/* This rank's block of A (device arrays, kept by reference) and its shard of B's row_ptr
+ * (device, bounds[rank+1]-bounds[rank]+1 entries, rebased to 0; copied). */
+int mhb_shard_set_A(mhb_shard_t s, int M_local, int nnzA, const int *dA_ptr, const int *dA_col,
+                    const int *dBown_ptr);
+int mhb_shard_export(mhb_shard_t s, int phase /* 1 or 2 */, void *blob /* MHB_SHARD_BLOB_BYTES */);
+int mhb_shard_import(mhb_shard_t s, int phase, const void *blobs /* world * MHB_SHARD_BLOB_BYTES */);
+/* Where this rank's shard of B lives (col: GLOBAL column ids; val: value_bytes each), and the
+ * image the SpGEMM reads: rows [*k0, *k1) of B, *nnz_image entries. */
+int mhb_shard_own_B(mhb_shard_t s, int **dB_col_own, void **dB_val_own, long long *nnz_own);
+int mhb_shard_image(mhb_shard_t s, int *k0, int *k1, long long *nnz_image, long long *halo_bytes_per_step);
+/* The exchange step (stream-ordered on the handle's stream, returns without synchronising). */
+int mhb_shard_exchange(mhb_shard_t s);
+/* Device-side barrier over all ranks (peer flags, stream-ordered): call between the end of a
+ * step and the next modification of B's shard, and to align ranks before timing. */
+int mhb_shard_barrier(mhb_shard_t s);
+/* mhb_symbolic / mhb_numeric_* for rows [r_lo, r_hi) of this rank's block against the image. */
+int mhb_shard_symbolic(mhb_shard_t s, int r_lo, int r_hi, int *dC_ptr, long long *nnzC);
+int mhb_shard_numeric_f64(mhb_shard_t s, const double *dA_val, int *dC_col, double *dC_val);
+int mhb_shard_numeric_f32(mhb_shard_t s, const float *dA_val, int *dC_col, float *dC_val);
+/* Publish this rank's nnz(C slice) of the step to every rank (one-sided, stream-ordered);
+ * mhb_shard_offsets waits for all of them: offset of this rank's slice and the total. */
+int mhb_shard_post_size(mhb_shard_t s, long long nnzC_local);
+int mhb_shard_offsets(mhb_shard_t s, long long *slice_offset, long long *nnzC_total,
+                      long long *all_sizes /* world entries, may be NULL */);
+
+/* NCCL from C++ (optional; libnccl.so.2 is loaded at run time): the north-star exchange
+ * "B is NCCL-broadcast over NVLink" for inputs where every rank needs all of B.
+ * mhb_nccl_unique_id on one rank -> [caller distributes the 128 bytes] -> mhb_shard_init_nccl
+ * on every rank -> mhb_shard_broadcast(buffer, bytes, root) each step, on the handle's stream. */
+int mhb_nccl_unique_id(void *id128);
+int mhb_shard_init_nccl(mhb_shard_t s, const void *id128);
+int mhb_shard_broadcast(mhb_shard_t s, void *dbuf, size_t bytes, int root);
 
 /* version / build info */
 const char *mhb_version(void);

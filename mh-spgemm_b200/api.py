@@ -34,8 +34,13 @@ ABI_SYMBOLS = [
     "mhb_symbolic", "mhb_numeric_f64", "mhb_numeric_f32", "mhb_spgemm_f64", "mhb_spgemm_f32",
     "mhb_device_free", "mhb_device_alloc", "mhb_memcpy_h2d", "mhb_memcpy_d2h", "mhb_spgemm_host_f64", "mhb_spgemm_host_f32", "mhb_host_alloc", "mhb_host_free",
     "mhb_form_mask_matrix_B", "mhb_get_row_info", "mhb_get_bins", "mhb_get_timing", "mhb_get_stats",
-    "mhb_transpose_f64", "mhb_transpose_f32",
+    "mhb_transpose_f64", "mhb_transpose_f32", "mhb_get_stream",
+    "mhb_shard_create", "mhb_shard_destroy", "mhb_shard_last_error", "mhb_shard_set_A", "mhb_shard_export",
+    "mhb_shard_import", "mhb_shard_own_B", "mhb_shard_image", "mhb_shard_exchange", "mhb_shard_barrier",
+    "mhb_shard_symbolic", "mhb_shard_numeric_f64", "mhb_shard_numeric_f32", "mhb_shard_post_size",
+    "mhb_shard_offsets", "mhb_nccl_unique_id", "mhb_shard_init_nccl", "mhb_shard_broadcast",
 ]
+SHARD_BLOB_BYTES = 128
 
 
 class Timing(C.Structure):
@@ -96,6 +101,26 @@ def load_library() -> C.CDLL:
                                   C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
     for n in ("mhb_transpose_f64", "mhb_transpose_f32"):
         getattr(L, n).argtypes = [vp, ip, ip, ip, vp, vp, vp, vp, vp, vp]
+    L.mhb_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.mhb_shard_create.argtypes = [C.POINTER(vp), vp, ip, ip, ip, ip, ip, C.POINTER(ll)]
+    L.mhb_shard_destroy.argtypes = [vp]
+    L.mhb_shard_last_error.argtypes = [vp]
+    L.mhb_shard_last_error.restype = C.c_char_p
+    L.mhb_shard_set_A.argtypes = [vp, ip, ip, vp, vp, vp]
+    L.mhb_shard_export.argtypes = [vp, ip, vp]
+    L.mhb_shard_import.argtypes = [vp, ip, vp]
+    L.mhb_shard_own_B.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
+    L.mhb_shard_image.argtypes = [vp, C.POINTER(ip), C.POINTER(ip), C.POINTER(ll), C.POINTER(ll)]
+    L.mhb_shard_exchange.argtypes = [vp]
+    L.mhb_shard_barrier.argtypes = [vp]
+    L.mhb_shard_symbolic.argtypes = [vp, ip, ip, vp, C.POINTER(ll)]
+    L.mhb_shard_numeric_f64.argtypes = [vp, vp, vp, vp]
+    L.mhb_shard_numeric_f32.argtypes = [vp, vp, vp, vp]
+    L.mhb_shard_post_size.argtypes = [vp, ll]
+    L.mhb_shard_offsets.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(ll)]
+    L.mhb_nccl_unique_id.argtypes = [vp]
+    L.mhb_shard_init_nccl.argtypes = [vp, vp]
+    L.mhb_shard_broadcast.argtypes = [vp, vp, C.c_size_t, ip]
     L.mhb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.mhb_host_free.argtypes = [vp]
     L.mhb_form_mask_matrix_B.argtypes = [vp, ip, ip, ip, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
@@ -105,7 +130,7 @@ def load_library() -> C.CDLL:
     L.mhb_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.mhb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     for n in ABI_SYMBOLS:
-        if n not in ("mhb_version", "mhb_last_error"):
+        if n not in ("mhb_version", "mhb_last_error", "mhb_shard_last_error"):
             getattr(L, n).restype = ip
     return L
 
@@ -326,6 +351,32 @@ def _d2h(dev_ptr: int, count: int, dtype) -> np.ndarray:
         if rc:
             raise MhbError(rc, "mhb_memcpy_d2h failed")
     return out
+
+
+class DeviceView:
+    """A non-owning view of `count` items at a raw device pointer (e.g. a rank's shard of B
+    inside its peer window); same duck type as DeviceArray.  upload() is CSR::H2D's copy."""
+
+    def __init__(self, ptr: int, count: int, dtype):
+        self.ptr, self.count, self.dtype = int(ptr), int(count), np.dtype(dtype)
+        self.nbytes = self.count * self.dtype.itemsize
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def numel(self) -> int:
+        return self.count
+
+    def numpy(self) -> np.ndarray:
+        return _d2h(self.ptr, self.count, self.dtype)
+
+    def upload(self, host: np.ndarray):
+        host = np.ascontiguousarray(host, self.dtype)
+        assert host.size == self.count
+        if self.nbytes:
+            rc = _lib().mhb_memcpy_h2d(C.c_void_p(self.ptr), _hp(host), self.nbytes)
+            if rc:
+                raise MhbError(rc, "mhb_memcpy_h2d failed")
 
 
 class DeviceArray:

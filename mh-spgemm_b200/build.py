@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmhb_spgemm.so")
-SOURCES = ["mhb_capi.cu", "mhb_compat.cu"]
+SOURCES = ["mhb_capi.cu", "mhb_compat.cu", "mhb_shard.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *srcs]
+    cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *srcs, "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

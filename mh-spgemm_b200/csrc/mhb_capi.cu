@@ -1201,6 +1201,14 @@ extern "C"
         return MHB_OK;
     }
 
+    int mhb_get_stream(mhb_handle_t h, void **cuda_stream)
+    {
+        if (!h || !cuda_stream)
+            return MHB_ERR_ARG;
+        *cuda_stream = (void *)h->stream;
+        return MHB_OK;
+    }
+
     int mhb_set_option(mhb_handle_t h, const char *key, long long value)
     {
         if (!h || !key)

@@ -212,12 +212,22 @@ class ShardedSpGEMM:
         self.tool, self.rank, self.world = tool, rank, world
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.sizes = SliceSizes(rank, world, self.device)
+        self._bind_stream()
+
+    def _bind_stream(self):
+        """The exchange (torch.distributed) runs on torch's current stream; the Tool must launch
+        on the same stream, or symbolic / numeric could read B before the exchange has landed
+        and torch's caching allocator would not know about the writes into ccol / cval."""
+        if self.device.type == "cuda":
+            import torch
+            self.tool.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def step(self, A_blk, Bbuf, K: int, N: int, nnzB: int, val_dtype, src: int = 0):
         """One sharded SpGEMM.  A_blk = (M_local, ptr, col, val) device tensors of this
         rank's rows; Bbuf = packed B image (valid on `src`, receive buffer elsewhere).
         Returns (C_ptr, C_col, C_val, slice_offset, total_nnz)."""
         import torch
+        self._bind_stream()
         exchange_B(Bbuf, self.world, src)
         bp, bc, bv = b_views(Bbuf, K, nnzB, val_dtype)
         Ml, ap, ac, av = A_blk
@@ -233,6 +243,7 @@ class ShardedSpGEMM:
         """Same as step() with B row-sharded like A: gather the referenced row range of B
         (RangeExchange), multiply the local block (whose columns were shifted by -k0)."""
         import torch
+        self._bind_stream()
         bp, bc, bv = plan.run(own_col, own_val)
         Ml, ap, ac, av = A_blk_shifted
         cp, nnz = self.tool.symbolic(Ml, plan.K_local, N, ap, ac, bp, bc[:plan.nnz_local])
@@ -244,6 +255,131 @@ class ShardedSpGEMM:
         else:  # sizes stay on the device; SliceSizes.offsets() turns them into offsets on demand
             off, total = None, self.sizes.gather(nnz)
         return cp, ccol[:nnz], cval[:nnz], off, total
+
+
+class Shard:
+    """One rank of the row-sharded SpGEMM behind the C ABI (``mhb_shard_*``, include/mhb_spgemm.h):
+    B is row-sharded like A, every rank keeps a contiguous image of the B rows its block references
+    in a CUDA-IPC window and pulls the pieces it does not own out of the owners' windows over
+    NVLink -- one-sided, no send/recv pairing, no host-side collective inside a step.
+
+    `allgather(bytes) -> list[bytes]` is the caller's transport for the two fixed-size set-up
+    blobs (default: torch.distributed.all_gather_object on the default group)."""
+
+    def __init__(self, tool, rank: int, world: int, K: int, N: int, val_dtype, bounds, allgather=None):
+        import ctypes as C
+        from .api import MhbError
+        self.C, self.MhbError = C, MhbError
+        self.tool, self.L, self.rank, self.world = tool, tool.L, rank, world
+        self.val_dtype = np.dtype(val_dtype)
+        self.s = C.c_void_p()
+        b = (C.c_longlong * (world + 1))(*[int(x) for x in bounds])
+        rc = self.L.mhb_shard_create(C.byref(self.s), tool.h, rank, world, K, N, self.val_dtype.itemsize, b)
+        if rc:
+            raise MhbError(rc, "mhb_shard_create failed (bad bounds / world > 8?)")
+        self._allgather = allgather or _allgather_object
+        self._keep = None
+
+    def _chk(self, rc):
+        if rc:
+            raise self.MhbError(rc, self.L.mhb_shard_last_error(self.s).decode())
+
+    def close(self):
+        if self.s:
+            self.L.mhb_shard_destroy(self.s)
+            self.s = self.C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up (collective) ---------------------------------------------------------------
+    def build(self, M_local: int, dA_ptr, dA_col, dBown_ptr):
+        """Plan of this rank: A's block (device int32 arrays, GLOBAL column ids; kept by
+        reference) and the row_ptr of its shard of B (rebased to 0).  Collective: two
+        all-gathers of 128-byte blobs through the caller's transport."""
+        from .api import SHARD_BLOB_BYTES
+        C = self.C
+        self._keep = (dA_ptr, dA_col, dBown_ptr)
+        self.M_local = M_local
+        self._chk(self.L.mhb_shard_set_A(self.s, M_local, dA_col.numel(), dA_ptr.data_ptr(), dA_col.data_ptr(),
+                                         dBown_ptr.data_ptr()))
+        for phase in (1, 2):
+            blob = (C.c_char * SHARD_BLOB_BYTES)()
+            self._chk(self.L.mhb_shard_export(self.s, phase, blob))
+            parts = self._allgather(bytes(blob))
+            assert len(parts) == self.world and all(len(x) == SHARD_BLOB_BYTES for x in parts)
+            self._chk(self.L.mhb_shard_import(self.s, phase, b"".join(parts)))
+        return self
+
+    def own_B(self):
+        """(col view, val view) of this rank's shard of B inside its window: the caller writes
+        GLOBAL column ids and values there (DeviceView.upload from the host, or a device copy)."""
+        from .api import DeviceView
+        C = self.C
+        pc, pv, n = C.c_void_p(), C.c_void_p(), C.c_longlong()
+        self._chk(self.L.mhb_shard_own_B(self.s, C.byref(pc), C.byref(pv), C.byref(n)))
+        return DeviceView(pc.value or 0, n.value, np.int32), DeviceView(pv.value or 0, n.value, self.val_dtype)
+
+    def image(self):
+        """(k0, k1, nnz_image, halo_bytes_per_step): the B rows this rank's SpGEMM reads."""
+        C = self.C
+        k0, k1, n, hb = C.c_int(), C.c_int(), C.c_longlong(), C.c_longlong()
+        self._chk(self.L.mhb_shard_image(self.s, C.byref(k0), C.byref(k1), C.byref(n), C.byref(hb)))
+        return k0.value, k1.value, n.value, hb.value
+
+    # ---- per step (stream-ordered on the Tool's stream) ---------------------------------------
+    def exchange(self):
+        self._chk(self.L.mhb_shard_exchange(self.s))
+
+    def barrier(self):
+        self._chk(self.L.mhb_shard_barrier(self.s))
+
+    def symbolic(self, r_lo: int, r_hi: int, dC_ptr):
+        nnz = self.C.c_longlong()
+        self._chk(self.L.mhb_shard_symbolic(self.s, r_lo, r_hi, dC_ptr.data_ptr(), self.C.byref(nnz)))
+        return int(nnz.value)
+
+    def numeric_into(self, dA_val, dC_col, dC_val):
+        f = self.L.mhb_shard_numeric_f64 if self.val_dtype.itemsize == 8 else self.L.mhb_shard_numeric_f32
+        self._chk(f(self.s, dA_val.data_ptr(), dC_col.data_ptr(), dC_val.data_ptr()))
+
+    def post_size(self, nnz_local: int):
+        self._chk(self.L.mhb_shard_post_size(self.s, int(nnz_local)))
+
+    def offsets(self):
+        """(offset of this rank's slice in the global col / val arrays, total nnz(C), all sizes)."""
+        C = self.C
+        off, tot = C.c_longlong(), C.c_longlong()
+        sizes = (C.c_longlong * self.world)()
+        self._chk(self.L.mhb_shard_offsets(self.s, C.byref(off), C.byref(tot), sizes))
+        return int(off.value), int(tot.value), [int(x) for x in sizes]
+
+    # ---- NCCL from C++ (the broadcast layout) ---------------------------------------------------
+    def init_nccl(self):
+        """ncclCommInitRank inside the library; the 128-byte id travels through `allgather`."""
+        C = self.C
+        ident = (C.c_char * 128)()
+        if self.rank == 0:
+            rc = self.L.mhb_nccl_unique_id(ident)
+            if rc:
+                raise self.MhbError(rc, "mhb_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+        ident = self._allgather(bytes(ident))[0]
+        self._chk(self.L.mhb_shard_init_nccl(self.s, ident))
+
+    def broadcast(self, dbuf, nbytes: int, root: int = 0):
+        self._chk(self.L.mhb_shard_broadcast(self.s, dbuf.data_ptr(), nbytes, root))
+
+
+def _allgather_object(blob: bytes):
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [blob]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, blob)
+    return out
 
 
 def slice_rows_by_products(work: np.ndarray, r0: int, r1: int, cap: int = 2**31 - 1) -> list[tuple[int, int]]:
