@@ -156,25 +156,50 @@ def cpu_baseline(A: CSR, B: CSR, intprod: int, budget_s: float = 12.0) -> dict:
 
 
 # ---------------------------------------------------------------------------------------
+L2_NOTE = "flushed between timed steps (256 MiB write)"
+
+# numeric bin -> the kernel that serves it (csrc/mhb_capi.cu launch_numeric_bins)
+NUM_KERNEL = {"WIN_COMPACT": "k_num_compact_rowtwins", "WIN_WARP": "k_num_win_group<32>", "WIN_G8": "k_num_win_group<8>",
+              "WIN_BLOCK_S": "k_num_win_block", "WIN_BLOCK_L": "k_num_win_block", "H_G8": "k_num_hash_group<8>",
+              "H_WARP_XS": "k_num_hash_list<wrows>", "H_WARP_S": "k_num_hash_list<wrows>", "H_WARP_M": "k_num_hash_list",
+              "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_L": "k_num_hash_block",
+              "H_GLOBAL": "k_num_hash_block(pool)", "TINY": "k_num_tiny"}
+
+
+def captured_traffic(workload: str, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from a
+    committed `ncu --set full` capture (profiles/r2_traffic.json names the capture); never a
+    literal in this file, and null for anything that has no capture."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(workload)
+    except (OSError, ValueError):
+        rec = None
+    if not rec or world != 1:
+        return None, None
+    return int(rec["traffic"]), {k: rec[k] for k in ("kernel", "capture") if k in rec}
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's own kernels (oracle/_ref) on the N=1 workload."""
+    """--impl reference: the reference's own kernels (oracle/_ref) on the SAME matrix our arm
+    multiplies at this N (the reference is single-GPU: rank 0 runs the whole N x matrix)."""
     if rank != 0:
         return
-    A, cfg = make_workload(args.workload)
+    A, cfg = make_workload(args.workload, scale=max(1, args.gpus))
     intprod = int(np.diff(A.ptr).astype(np.int64)[A.col].sum())
     base = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(cfg, parallelism="single GPU (the reference has no multi-GPU path)")}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.workload == "G" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "parallelism": "single GPU (the reference has no multi-GPU path)"}
     from oracle import Reference
     out = None
     if Reference.available():
         # separate process: a fault inside the reference must not take the bench down
         code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import mh_spgemm_b200\n"
                 "import bench; from oracle import Reference\n"
-                "A, _ = bench.make_workload(%r)\n"
+                "A, _ = bench.make_workload(%r, scale=%d)\n"
                 "R = Reference().spgemm(A, A, reps=%d, warmup=%d, e2e_reps=%d)\n"
                 "print('REFJSON', json.dumps(dict(nnz=R['nnz'], ms_device=R['ms_device'], ms_e2e=R['ms_e2e'], ms_min=R['ms_device_min'])))\n"
-                % (ROOT, args.workload, args.steps, args.warmup, max(2, min(args.steps, 5))))
+                % (ROOT, args.workload, max(1, args.gpus), args.steps, args.warmup, max(2, min(args.steps, 5))))
         p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500)
         for ln in p.stdout.splitlines():
             if ln.startswith("REFJSON"):
@@ -189,6 +214,9 @@ def run_reference(args, rank):
         e = 2.0 * intprod / out["ms_e2e"] / 1e6
         base.update(value=round(v, 3), ms_per_step=round(out["ms_device"], 4),
                     ms_per_step_best=round(out.get("ms_min", 0.0), 4),
+                    config=dict(cfg, intprod=intprod, nnzC=nnzC),
+                    l2="not flushed by the harness: every MH_spgemm call allocates its workspace and C afresh "
+                       "(9 cudaMalloc, 12 stream creations), which is the reference's own stock path",
                     e2e={"value": round(e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                          "ms_per_step": round(out["ms_e2e"], 3)},
                     cpu_baseline={"value": round(v, 3), "unit": UNIT, "cores": 1, "kind": "reference",
@@ -197,11 +225,115 @@ def run_reference(args, rank):
                                             "per-call allocations, std::chrono, median"},
                     gpu_launches=0)
     else:
+        from oracle import Oracle
+        nnzC = int(Oracle().symbolic(A, A)[-1])
         cb = cpu_baseline(A, A, intprod)
         base.update(value=cb["value"], ms_per_step=cb["ms_per_step"], cpu_baseline=cb,
+                    config=dict(cfg, intprod=intprod, nnzC=nnzC),
                     e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     gpu_launches=0)
     print(json.dumps(base), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+def check_slice_against_oracle(Ablk, B, cp, cc, cv, rtol=1e-12) -> dict:
+    """This rank's slice of C against the host oracle on the same rows (outside the timed
+    region): row_ptr and col_idx bit-exact, values within rtol."""
+    from oracle import Oracle
+    orc = Oracle()
+    Cp, Cc, Cv = orc.spgemm(Ablk, B)
+    ok_struct = bool(np.array_equal(cp.astype(np.int64), Cp) and np.array_equal(cc, Cc))
+    bad = -1
+    if ok_struct:
+        bad, _ = orc.compare(Ablk.M, (cp, cc, cv), (Cp, Cc, Cv), rtol)
+    return {"structure": ok_struct, "values_bad": int(bad), "nnz": int(Cp[-1])}
+
+
+def check_slice_invariants(torch, Aslice, B, cp, cc, cv) -> dict:
+    """Size-independent checks for slices too large for the host oracle (the large R-MAT):
+    column ids ascending inside every row and in range; row sums equal A (B 1) (linearity)."""
+    nnz = int(cc.numel())
+    ok_sorted = True
+    if nnz > 1:
+        d = cc[1:] - cc[:-1]
+        starts = cp[1:-1].long()
+        starts = starts[(starts > 0) & (starts < nnz)]
+        d[starts - 1] = 1
+        ok_sorted = bool((d > 0).all().item()) and int(cc.min().item()) >= 0 and int(cc.max().item()) < B.N
+        del d
+    blen = np.diff(B.ptr)
+    y = np.add.reduceat(np.append(B.val, 0.0), np.minimum(B.ptr[:-1], B.nnz))
+    y[blen == 0] = 0.0
+    t = Aslice.val * y[Aslice.col]
+    want = np.add.reduceat(np.append(t, 0.0), np.minimum(Aslice.ptr[:-1], Aslice.nnz))
+    want[np.diff(Aslice.ptr) == 0] = 0.0
+    lens = (cp[1:] - cp[:-1]).long()
+    got = torch.segment_reduce(cv[:nnz], "sum", lengths=lens, unsafe=True).cpu().numpy()
+    got[np.diff(cp.cpu().numpy()) == 0] = 0.0
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))) if want.size else 0.0
+    return {"sorted_in_range": ok_sorted, "rowsum_max_rel_err": err}
+
+
+def suite_breadth(tool, budget_s=150.0) -> dict:
+    """BASELINE configs[3] in one number: C = A*A on the twelve small suite analogs, ours
+    (device time, mask build included, median of 3) vs the reference's kernels on the same box
+    (oracle/_ref in a subprocess, best of 5), structure compared by SHA-256.  Outside the timed
+    region; stops when the time budget is used up."""
+    import hashlib
+    from mh_spgemm_b200 import api
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    from oracle import Reference
+    if not Reference.available():
+        return {"unavailable": "oracle/_ref not built"}
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, np.int32).tobytes()).hexdigest()  # noqa: E731
+    t_end = time.time() + budget_s
+    rows, ratios = {}, []
+    for name in cases.SUITE12:
+        if time.time() > t_end:
+            break
+        A = G.suite(name)
+        ip = int(np.diff(A.ptr).astype(np.int64)[A.col].sum())
+        dAp, dAc, dAv = api.DeviceArray(A.ptr), api.DeviceArray(A.col), api.DeviceArray(A.val)
+        ts = []
+        for it in range(4):
+            dCp, nnzC = tool.symbolic(A.M, A.N, A.N, dAp, dAc, dAp, dAc)
+            dCc, dCv = tool.numeric(dAv, dAv, nnzC)
+            ts.append(tool.timing.total)
+            if it < 3:
+                dCc.free(), dCv.free(), dCp.free()
+        ours_ms = float(np.median(ts[1:]))
+        mine = (sha(dCp.numpy()), sha(dCc.numpy()[:nnzC]))
+        for d in (dCp, dCc, dCv, dAp, dAc, dAv):
+            d.free()
+        path = f"/dev/shm/mhb_suite_{os.getpid()}.npz"
+        np.savez(path, M=A.M, N=A.N, ptr=A.ptr, col=A.col, val=A.val)
+        code = ("import sys, json, hashlib, numpy as np; sys.path.insert(0, %r); import mh_spgemm_b200\n"
+                "from mh_spgemm_b200.csr import CSR; from oracle import Reference\n"
+                "z = np.load(%r); A = CSR(int(z['M']), int(z['N']), z['ptr'], z['col'], z['val'])\n"
+                "R = Reference().spgemm(A, A, reps=5, warmup=1, e2e_reps=0)\n"
+                "h = lambda a: hashlib.sha256(np.ascontiguousarray(a, np.int32).tobytes()).hexdigest()\n"
+                "print('REFJSON', json.dumps(dict(ms=R['ms_device_min'], sp=h(R['ptr']), sc=h(R['col']))))\n" % (ROOT, path))
+        rec = {"ours_ms": round(ours_ms, 3), "ours_gflops": round(2 * ip / ours_ms / 1e6, 1)}
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+            r = [json.loads(ln[8:]) for ln in p.stdout.splitlines() if ln.startswith("REFJSON")]
+            if r:
+                rec.update(ref_ms=round(r[0]["ms"], 3), speedup=round(r[0]["ms"] / ours_ms, 2),
+                           structure_equal=bool((r[0]["sp"], r[0]["sc"]) == mine))
+                ratios.append(r[0]["ms"] / ours_ms)
+            else:
+                rec["ref_error"] = (p.stdout + p.stderr)[-160:]
+        except subprocess.TimeoutExpired:
+            rec["ref_error"] = "timeout"
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+        rows[name] = rec
+    geo = float(np.exp(np.mean(np.log(ratios)))) if ratios else None
+    return {"suite_geomean_vs_reference": None if geo is None else round(geo, 3), "matrices": len(ratios),
+            "all_structure_equal": all(r.get("structure_equal", False) for r in rows.values() if "ref_ms" in r),
+            "per_matrix": rows}
 
 
 # ---------------------------------------------------------------------------------------
@@ -213,10 +345,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="F", choices=["F", "P", "R", "G"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="range", choices=["range", "broadcast"],
-                    help="N>1: 'range' = B row-sharded like A, each rank gathers the B rows its block "
-                         "references (halo for FEM, all-gather for graphs); 'broadcast' = B on rank 0, "
-                         "ncclBroadcast every step")
+    ap.add_argument("--no-suite", action="store_true", help="skip the 12-matrix breadth check (N=1, workload F only)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "broadcast", "sendrecv"],
+                    help="N>1: 'peer' = B row-sharded like A, every rank pulls the B rows its block references out of "
+                         "the owners' CUDA-IPC windows (mhb_shard_*, one-sided over NVLink); 'broadcast' = B on "
+                         "rank 0, ncclBroadcast from C++ every step (the north-star wording); 'sendrecv' = the "
+                         "round-1 path, grouped NCCL send/recv driven by torch.distributed")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -228,8 +363,8 @@ def main():
     import torch
     import torch.distributed as dist
     from mh_spgemm_b200 import api
-    from mh_spgemm_b200.distributed import (RangeExchange, ShardedSpGEMM, column_range, pack_b, partition_rows,
-                                            row_work)
+    from mh_spgemm_b200.distributed import (RangeExchange, Shard, ShardedSpGEMM, SliceSizes, b_views, column_range,
+                                            pack_b, partition_rows, row_work, slice_rows_fast)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -241,7 +376,7 @@ def main():
 
     # ---- workload: identical seeded matrix on every rank, rows sharded by product count ----
     strong = args.workload == "G"  # fixed matrix split over the ranks (strong scaling)
-    A, cfg = make_workload(args.workload, scale=world)
+    A, cfg = make_workload(args.workload, scale=1 if strong else world)
     B = A
     work = row_work(A, B)
     intprod = int(work.sum())
@@ -252,75 +387,106 @@ def main():
     stream = torch.cuda.current_stream()
     tool.set_stream(stream.cuda_stream)
     dt = torch.float64
-    a_dev = (Ablk.M, torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
-             torch.from_numpy(Ablk.val).to(dev))
-    sh = ShardedSpGEMM(tool, rank, world, dev)
+    a_ptr, a_col, a_val = (torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
+                           torch.from_numpy(Ablk.val).to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    use_range = world > 1 and args.exchange == "range"
-    if use_range:
-        kr = [column_range(A.rows(int(bounds[r]), int(bounds[r + 1]))) for r in range(world)]
-        plan = RangeExchange(rank, world, bounds, kr, B.ptr, dt, dev)
-        a_shift = (a_dev[0], a_dev[1], a_dev[2] - plan.k0, a_dev[3])
-        exch_bytes = plan.bytes_received
-        # B = A is sharded like A: this rank's shard of B is its own block of A.  It is kept
-        # inside the gathered image (own_views), so a step only receives the halo pieces.
-        own_col, own_val = plan.own_views()
-        if own_col.numel() == a_dev[2].numel():
-            own_col.copy_(a_dev[2])
-            own_val.copy_(a_dev[3])
-        else:  # the block does not reference all of its own rows of B: keep the shard separate
-            own_col, own_val = a_dev[2], a_dev[3]
-        nnz_box = {}
+    # rows of this rank cut into slices of < 2^31 products (local int32 row_ptr per slice, int64 offsets)
+    slices = [(a - r0, b - r0) for a, b in slice_rows_fast(work, r0, r1, cap=(1 << 31) - 1)] if r1 > r0 else [(0, 0)]
+    mode = "single" if world == 1 else args.exchange
+    sh = sizes = None
+    exch_bytes = 0
+    k0, k1 = 0, B.M
+
+    def multiply(sym, num):
+        """symbolic + allocation + numeric per slice; returns the last slice and the rank's nnz."""
+        total, last = 0, None
+        for s0, s1 in slices:
+            cp = torch.empty(s1 - s0 + 1, dtype=torch.int32, device=dev)
+            nnz = sym(s0, s1, cp)
+            ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+            cval = torch.empty(max(nnz, 1), dtype=dt, device=dev)
+            num(ccol, cval)
+            total += nnz
+            last = (s0, s1, cp, ccol[:nnz], cval[:nnz])
+        return last, total
+
+    if mode == "single":
+        def one_step():  # B = A: one copy on the device, aliasing visible to the library
+            return multiply(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_ptr,
+                                                                  a_col, cp),
+                            lambda cc, cv: tool.numeric_into(a_val, a_val, cc, cv))
+    elif mode == "peer":
+        Bown = B.rows(r0, r1)  # B = A is sharded like A
+        dBp = torch.from_numpy(Bown.ptr).to(dev)
+        sh = Shard(tool, rank, world, B.M, B.N, np.float64, bounds).build(Ablk.M, a_ptr, a_col, dBp)
+        col_own, val_own = sh.own_B()
+        col_own.upload(Bown.col)
+        val_own.upload(Bown.val)
+        k0, k1, _, exch_bytes = sh.image()
 
         def one_step():
-            out_ = sh.step_range(a_shift, plan, own_col, own_val, B.N, dt, offsets_on_host=False)
-            nnz_box["total"] = out_[4]
-            return out_
-    else:
+            sh.exchange()
+            last, total = multiply(lambda s0, s1, cp: sh.symbolic(s0, s1, cp),
+                                   lambda cc, cv: sh.numeric_into(a_val, cc, cv))
+            sh.post_size(total)
+            return last, total
+    elif mode == "broadcast":
+        sh = Shard(tool, rank, world, B.M, B.N, np.float64, bounds)
+        sh.init_nccl()
+        sizes = SliceSizes(rank, world, dev)
         packed, _ = pack_b(B)
         Bbuf = packed.to(dev) if rank == 0 else torch.empty_like(packed, device=dev)
-        exch_bytes = 0 if world == 1 else packed.numel()
+        exch_bytes = 0 if rank == 0 else packed.numel()
+        bp, bc, bv = b_views(Bbuf, B.M, B.nnz, dt)
 
         def one_step():
-            return sh.step(a_dev, Bbuf, B.M, B.N, B.nnz, dt, src=0)
+            sh.broadcast(Bbuf, Bbuf.numel(), 0)  # ncclBroadcast issued from C++ on the Tool's stream
+            last, total = multiply(
+                lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, bp, bc, cp),
+                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
+            sizes.gather(total)
+            return last, total
+    else:  # sendrecv: the round-1 exchange (torch.distributed grouped send/recv), kept as the fallback
+        kr = [column_range(A.rows(int(bounds[r]), int(bounds[r + 1]))) for r in range(world)]
+        plan = RangeExchange(rank, world, bounds, kr, B.ptr, dt, dev)
+        a_shift = a_col - plan.k0
+        k0, k1 = plan.k0, plan.k1
+        exch_bytes = plan.bytes_received
+        own_col, own_val = plan.own_views()
+        if own_col.numel() == a_col.numel():
+            own_col.copy_(a_col)
+            own_val.copy_(a_val)
+        else:
+            own_col, own_val = a_col, a_val
+        sizes = SliceSizes(rank, world, dev)
 
-    if strong:
-        # nnz(C) of a rank can exceed int32: cut the local rows into slices of < 2^31 products,
-        # one SpGEMM per slice (local int32 row_ptr, int64 offsets), C slices are not retained
-        from mh_spgemm_b200.distributed import b_views, exchange_B, slice_offsets, slice_rows_fast
-        slices = slice_rows_fast(work, r0, r1, cap=(1 << 31) - 1)
-        slices = [(a - r0, b - r0) for a, b in slices]
+        def one_step():
+            bp, bc, bv = plan.run(own_col, own_val)
+            last, total = multiply(
+                lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, plan.K_local, B.N, a_ptr[s0:], a_shift, bp,
+                                                      bc[:plan.nnz_local], cp),
+                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
+            sizes.gather(total)
+            return last, total
 
-        def one_step():  # noqa: F811
-            if use_range:
-                bp, bc, bv = plan.run(own_col, own_val)
-                bc = bc[:plan.nnz_local]
-                ac, K_loc = a_shift[2], plan.K_local
-            else:
-                exchange_B(Bbuf, world, 0)
-                bp, bc, bv = b_views(Bbuf, B.M, B.nnz, dt)
-                ac, K_loc = a_dev[2], B.M
-            total_local = 0
-            for s0, s1 in slices:
-                cp, nnz = tool.symbolic(s1 - s0, K_loc, B.N, a_dev[1][s0:s1 + 1], ac, bp, bc)
-                ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-                cval = torch.empty(max(nnz, 1), dtype=dt, device=dev)
-                tool.numeric_into(a_dev[3], bv, ccol, cval)
-                total_local += nnz
-                last = (cp, ccol[:nnz], cval[:nnz])
-            off, total = slice_offsets(total_local, rank, world, dev)
-            return last[0], last[1], last[2], off, total
+    def totals():
+        if mode == "single":
+            return 0, nnz_local, [nnz_local]
+        if mode == "peer":
+            return sh.offsets()
+        off, tot = sizes.offsets()
+        return off, tot, None
 
     # the very first call is timed too: cold workspace (allocations), cold caches, module load
     cold0, cold1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cold0.record(stream)
-    out = one_step()
+    last, nnz_local = one_step()
     cold1.record(stream)
     torch.cuda.synchronize()
     cold_ms = cold0.elapsed_time(cold1)
     for _ in range(max(args.warmup - 1, 0)):
-        out = one_step()
-    nnzC_total = out[4].offsets()[1] if hasattr(out[4], "offsets") else int(out[4])
+        last, nnz_local = one_step()
+    slice_off, nnzC_total, all_sizes = totals()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -332,16 +498,19 @@ def main():
     torch.cuda.synchronize()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the event pair)
+        if mode == "peer":
+            sh.barrier()       # ranks leave the flush together: no start-time skew inside the event pair
         ev[k][0].record(stream)
-        one_step()
+        last, nnz_local = one_step()
         ev[k][1].record(stream)
         num_ms.append(tool.timing.Numeric)
-        launches += tool.stats["gpu_launches"]
+        launches += tool.stats["gpu_launches"] * len(slices) + (3 if mode == "peer" else 0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    own_ms = float(step_ms.mean().item())
     if world > 1:
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
     step_ms = step_ms.cpu().numpy()
@@ -349,14 +518,63 @@ def main():
     timing = tool.timing.as_dict()
     stats = tool.stats
 
+    # ---- parity, outside the timed region, on every rank and at every N ----
+    parity = None
+    if not args.no_parity:
+        s0, s1, cp, cc, cv = last
+        if strong:
+            inv = check_slice_invariants(torch, Ablk.rows(s0, s1), B, cp, cc, cv)
+            okv = inv["sorted_in_range"] and inv["rowsum_max_rel_err"] < 1e-9
+            mine = torch.tensor([1.0 if okv else 0.0, inv["rowsum_max_rel_err"]], dtype=torch.float64, device=dev)
+        else:
+            chk = check_slice_against_oracle(Ablk, B, cp.cpu().numpy(), cc.cpu().numpy(), cv.cpu().numpy())
+            okv = chk["structure"] and chk["values_bad"] == 0 and chk["nnz"] == nnz_local
+            mine = torch.tensor([1.0 if okv else 0.0, float(max(chk["values_bad"], 0))], dtype=torch.float64, device=dev)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allv, mine)
+        else:
+            allv = [mine]
+        oks = [bool(v[0].item() > 0.5) for v in allv]
+        sizes_ok = True
+        if not strong:  # slice sizes / offsets against the oracle's global row_ptr
+            from oracle import Oracle
+            gp = Oracle().symbolic(A, B) if rank == 0 else None
+            if rank == 0:
+                want = [int(gp[int(bounds[r + 1])] - gp[int(bounds[r])]) for r in range(world)]
+                sizes_ok = (nnzC_total == int(gp[-1])) and (all_sizes is None or list(all_sizes) == want)
+        if strong:
+            parity = {"checked": "every rank's last slice: columns ascending and in range, row sums == A(B 1)",
+                      "structure": "sorted + in range" if all(oks) else "FAILED",
+                      "rowsum_max_rel_err": max(float(v[1].item()) for v in allv), "ranks_ok": oks,
+                      "nnzC_total": nnzC_total}
+        else:
+            parity = {"checked": "every rank's slice vs the host oracle on the same rows; slice sizes vs the oracle's global row_ptr",
+                      "structure": "bit-exact" if all(oks) and sizes_ok else "FAILED", "values_rtol": 1e-12,
+                      "values_out_of_tol": int(sum(float(v[1].item()) for v in allv)), "ranks_ok": oks,
+                      "slice_sizes_ok": bool(sizes_ok)}
+        if not (all(oks) and sizes_ok):
+            if rank == 0:
+                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+            raise SystemExit(3)
+
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ----
     if strong:
         # the per-rank product can exceed the int32 contract of one host call; the device path
         # above is the measurement for this workload
         e2e_mean, h2d, d2h = None, 0, 0
     else:
-        PA = tool.pin(Ablk)
-        PB = PA if world == 1 else tool.pin(B)
+        if world == 1:
+            PA = PB = tool.pin(Ablk)
+            h2d = 4 * (Ablk.M + 1) + 12 * Ablk.nnz
+        else:  # a rank uploads its block of A and only the rows [k0, k1) of B that the block references
+            if mode in ("single", "broadcast"):
+                k0, k1 = column_range(Ablk)
+            from mh_spgemm_b200.csr import CSR as _CSR
+            PA = tool.pin(_CSR(Ablk.M, k1 - k0, Ablk.ptr, Ablk.col - k0, Ablk.val))
+            Bimg = B.rows(k0, k1)
+            PB = tool.pin(Bimg)
+            h2d = 4 * (Ablk.M + 1) + 12 * Ablk.nnz + 4 * (Bimg.M + 1) + 12 * Bimg.nnz
         tool.set_stream(None)
         e2e_ms = []
         for k in range(args.warmup + args.steps):
@@ -370,41 +588,44 @@ def main():
         if world > 1:
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_mean = float(e2e_t.item())
-        h2d = 4 * (Ablk.M + 1) + 12 * Ablk.nnz + (0 if world == 1 else 4 * (B.M + 1) + 12 * B.nnz)
         d2h = 4 * (Ablk.M + 1) + 12 * Ch.nnz
+        tool.set_stream(stream.cuda_stream)
 
     if rank == 0:
         ba = bytes_alg(A, B, nnzC_total)
         kern_ms = float(np.mean(num_ms))
-        # per-rank share of the compulsory traffic for the kernel's roofline (rank 0's slice)
-        ba_rank = bytes_alg(Ablk, B, int(out[1].numel()))
+        # per-rank share of the compulsory traffic for the kernel's roofline (rank 0's last slice)
+        ba_rank = bytes_alg(Ablk, B if mode in ("single", "broadcast") else B.rows(k0, k1), int(last[3].numel()))
         achieved = ba_rank / (kern_ms * 1e-3) / 1e9
+        nb = {k: v for k, v in stats["num_bins"].items() if v and k != "EMPTY"}
+        kernels = sorted({NUM_KERNEL.get(k, k) for k in nb})
+        traffic, capture = captured_traffic(args.workload, world)
+        par = {"single": "single GPU",
+               "peer": f"A row-sharded x{world} by product count; B row-sharded like A, every rank pulls the B rows its "
+                       "block references out of the owners' CUDA-IPC windows (one-sided, NVLink), C ABI mhb_shard_*",
+               "broadcast": f"A row-sharded x{world} by product count; B ncclBroadcast from rank 0 each step (C++), "
+                            "slice sizes by NCCL all-gather",
+               "sendrecv": f"A row-sharded x{world}; B row range by grouped NCCL send/recv (torch.distributed)"}[mode]
         line = {
             "metric": METRIC, "value": round(2.0 * intprod / ms / 1e6, 3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(cfg, intprod=intprod, nnzC=nnzC_total, l2="flushed between timed steps (256 MiB write)",
-                           parallelism=("single GPU" if world == 1 else
-                                        f"A row-sharded x{world} by product count; " +
-                                        ("B row-sharded like A, referenced row range gathered by NCCL send/recv "
-                                         "each step" if use_range else "B NCCL-broadcast from rank 0 each step")),
-                           exchange_bytes_received_rank0=exch_bytes),
-            "roofline": {"bound": "hbm", "kernel": "numeric (k_num_compact_rowtwins<double>)" if args.workload == "F"
-                         else "numeric (all bins)", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from
-                         # one `ncu --set full` capture (profiles/r1h_numcompact_final.md); other workloads: null
-                         "traffic": 243513856 if (args.workload == "F" and world == 1) else None,
-                         "bound_on_chip": "LSU data pipe 75 % (shared-memory accumulator traffic), issue 40 %, "
-                                          "14 warps/SM (profiles/r1h_numcompact_final.md)",
+            "config": dict(cfg, intprod=intprod, nnzC=nnzC_total),
+            "l2": L2_NOTE, "parallelism": par, "exchange_bytes_received_rank0": exch_bytes, "slices_rank0": len(slices),
+            "roofline": {"bound": "hbm",
+                         "kernel": "numeric: " + " + ".join(kernels) + ("" if len(kernels) == 1 else " (bins run concurrently)"),
+                         "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": traffic, "traffic_from_capture": capture,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ba_rank,
                          "kernel_ms": round(kern_ms, 4),
                          "pipeline_frac": round(ba / (ms * 1e-3) / 1e9 / peak / world, 4)},
             "e2e": (None if e2e_mean is None else
                     {"value": round(2.0 * intprod / e2e_mean / 1e6, 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_mean, 3)}),
+            "parity": parity,
             "gpu_launches": launches, "clocks": clocks,
             "stage_ms": {k: round(v, 4) for k, v in timing.items()},
+            "rank0_ms_per_step": round(own_ms, 4),
             # the reference's own total leaves the mask build out (src/Timing.cpp:39-42)
             "ms_per_step_reference_convention": round(ms - timing.get("Form_mask_matrix_B", 0.0), 4),
             "cold_first_call_ms": round(cold_ms, 3),
@@ -413,9 +634,26 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(A, B, intprod)
+        if world == 1 and args.workload == "F" and not args.no_suite:
+            line["suite"] = suite_breadth(tool)
         print(json.dumps(line), flush=True)
+    if sh is not None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sh.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def tool_symbolic_into(tool, M, K, N, a_ptr, a_col, b_ptr, b_col, cp):
+    """mhb_symbolic into a caller-owned row_ptr (the Tool wrapper allocates its own)."""
+    import ctypes as C
+    nnz = C.c_longlong()
+    tool._keep = (a_ptr, a_col, b_ptr, b_col, cp)
+    tool._chk(tool.L.mhb_symbolic(tool.h, M, K, N, a_col.numel(), a_ptr.data_ptr(), a_col.data_ptr(), b_col.numel(),
+                                  b_ptr.data_ptr(), b_col.data_ptr(), cp.data_ptr(), C.byref(nnz)))
+    return int(nnz.value)
 
 
 if __name__ == "__main__":

@@ -126,6 +126,7 @@ struct mhb_context
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
     int sym_twins = 1;                   // option "sym_twins": symbolic computes one row per run of twin rows of A
     int pdl = 1;                         // option "pdl": programmatic dependent launch of the main-stream chain
+    int mask_onepass = 1;                // option "mask_onepass": one-pass mask builder (0: the round-1 five-kernel chain)
     int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
@@ -308,6 +309,16 @@ int run_binning(mhb_context *h, int M, int nbins, int *bins, int size_at, int of
     return MHB_OK;
 }
 
+// The scalar block is followed, in the same allocation, by everything else that must be zero
+// when a call starts -- the chunk ticket and chunk status words of the chained scan and the
+// row-start flag words of the mask builder -- so that ONE memset per call clears them all.
+constexpr size_t kCtrlOffset = (size_t)SC_COUNT * 4;    // unsigned ticket (+ padding to 64 bytes)
+constexpr size_t kStatusOffset = kCtrlOffset + 64;      // unsigned long long status[nchunks]
+inline long long mask_words(long long nnz) { return (nnz + 31) / 32; }
+inline int mask_chunks(long long nnz) { return (int)((mask_words(nnz) + kMaskChunkWords - 1) / kMaskChunkWords); }
+inline size_t flags_offset(long long nnz) { return kStatusOffset + (size_t)(mask_chunks(nnz) + 1) * 8; }
+inline size_t scal_bytes(long long nnz) { return flags_offset(nnz) + (size_t)(mask_words(nnz) + 2) * 4; }
+
 int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
 {
     *grew = false;
@@ -330,7 +341,7 @@ int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
         {&h->bins_num, ((size_t)M + 1) * 4},
         {&h->blockhist, (size_t)MHB_MAX_BINS * (size_t)(cdiv(std::max(M, 1), kBinThreads) + 1) * 4},
         {&h->scan_tmp, (size_t)(cdiv(std::max<long long>(std::max<long long>(nW, (long long)M + 1), 1), kScanTile) + 2) * 8},
-        {&h->scal, (size_t)SC_COUNT * 4},
+        {&h->scal, scal_bytes(nnzB)},
     };
     for (auto &r : reqs)
     {
@@ -346,10 +357,28 @@ int build_mask_matrix(mhb_context *h, int K, int nnzB, const int *Bp, const int 
 {
     const long long nnz = nnzB;
     const long long nW = (nnz + 31) / 32;
-    unsigned *flags = h->flags.as<unsigned>();
     int *wp = h->wordprefix.as<int>();
     int *scal = h->scal.as<int>();
     long long *ntiles_dev = reinterpret_cast<long long *>(scal + SC_NTILES_LO);
+    if (h->mask_onepass)
+    {
+        // the caller has zeroed scal_bytes(nnzB) bytes at h->scal: scalars, ticket, status, flags
+        unsigned char *base = h->scal.as<unsigned char>();
+        unsigned *oflags = reinterpret_cast<unsigned *>(base + flags_offset(nnz));
+        if (nnz > 0)
+        {
+            LAUNCH(h, k_mask_rowstarts, cdiv(K, 256), 256, 0, K, Bp, oflags);
+            LAUNCH(h, k_mask_build, mask_chunks(nnz), kMaskThreads, 0, Bc, nnz, nW, oflags, wp, h->tilecol.as<int>(),
+                   h->tilemask.as<unsigned>(), reinterpret_cast<unsigned *>(base + kCtrlOffset),
+                   reinterpret_cast<unsigned long long *>(base + kStatusOffset), mask_chunks(nnz), ntiles_dev);
+        }
+        LAUNCH(h, k_mask_rows, cdiv((long long)K + 1, 256), 256, 0, K, nnz, Bp, Bc, (const unsigned *)oflags,
+               (const int *)wp, (const long long *)ntiles_dev, (const int *)h->tilecol.as<int>(),
+               (const unsigned *)h->tilemask.as<unsigned>(), h->tileptr.as<int>(), h->binfo.as<int4>(),
+               h->bsame.as<unsigned char>());
+        return MHB_OK;
+    }
+    unsigned *flags = h->flags.as<unsigned>();
     if (nnz > 0)
     {
         CU(cudaMemsetAsync(h->tilemask.p, 0, (size_t)nnz * 4, h->stream));
@@ -760,7 +789,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
         return rc;
     int *scal = h->scal.as<int>();
     int *hs = h->h_scal.as<int>();
-    CU(cudaMemsetAsync(scal, 0, SC_COUNT * 4, h->stream));
+    CU(cudaMemsetAsync(scal, 0, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4, h->stream));
     CU(cudaEventRecord(h->ev[EV_ALLOC], h->stream));
     // twin rows of A (same column list as the previous row): B's flags when A is B; otherwise
     // compared now on a helper stream, hidden behind the mask build that only needs B
@@ -1230,6 +1259,8 @@ extern "C"
             h->pdl = (int)value;
         else if (k == "count_probes")
             h->count_probes = (int)value;
+        else if (k == "mask_onepass")
+            h->mask_onepass = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")
@@ -1353,7 +1384,7 @@ extern "C"
         int rc = ensure_workspace(h, 0, K, nnzB, &grew);
         if (rc)
             return rc;
-        CU(cudaMemsetAsync(h->scal.p, 0, SC_COUNT * 4, h->stream));
+        CU(cudaMemsetAsync(h->scal.p, 0, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4, h->stream));
         rc = build_mask_matrix(h, K, nnzB, dB_ptr, dB_col);
         if (rc)
             return rc;

@@ -137,6 +137,254 @@ __global__ void __launch_bounds__(256) k_mask_fill(const int *__restrict__ Bc, l
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// One-pass builder (round 2): flags + scan + fill in ONE kernel that reads B.col ONCE.
+//
+//   k_mask_rowstarts   row-start bits into a zeroed flag array (shares one memset with the scalars)
+//   k_mask_build       per 2 048-nonzero chunk: tile-start flags, chunk tile count, decoupled
+//                      look-back for the tile index in front of the chunk (single-pass chained scan,
+//                      chunks taken in ticket order so a chunk only ever waits for chunks that
+//                      are already running), then tile columns and masks straight from the columns
+//                      still held in registers
+//   k_mask_rows        tile offsets + row descriptors + twin flags, one thread per row
+//
+// A tile run holds at most 32 nonzeros (distinct columns of one 32-column tile), so it spans
+// at most two 32-nonzero words.  The warp that owns the word where a run STARTS also reads the
+// leading lanes of the next word and writes the whole mask with one plain store: no atomicOr,
+// and tilemask needs no zero fill (round 1 cleared nnz(B) words per call).
+// ---------------------------------------------------------------------------------------
+constexpr int kMaskThreads = 256;
+constexpr int kMaskWordsPerWarp = 8;
+constexpr int kMaskChunkWords = (kMaskThreads / 32) * kMaskWordsPerWarp; // 64 words = 2 048 nonzeros
+
+// chunk status of the chained scan: (state << 62) | value
+constexpr unsigned long long kScanAggregate = 1ull << 62; // value = tiles of this chunk only
+constexpr unsigned long long kScanPrefix = 2ull << 62;    // value = tiles of all chunks up to and including this one
+constexpr unsigned long long kScanValueMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of chunk `chunk` (sum of the aggregates of all chunks in front of it), by
+// one warp: 32 predecessors per round, newest first; stops at the first one that already
+// knows its inclusive prefix.  Publishes this chunk's aggregate first and its inclusive
+// prefix last.  Returns the exclusive prefix in every lane.
+__device__ __forceinline__ long long chained_scan_lookback(unsigned long long *status, int chunk, long long aggregate)
+{
+    const int lane = lane_id();
+    if (lane == 0)
+        st_status(status + chunk, (chunk == 0 ? kScanPrefix : kScanAggregate) | (unsigned long long)aggregate);
+    long long excl = 0;
+    int idx = chunk - 1;
+    while (idx >= 0)
+    {
+        const int j = idx - lane;
+        unsigned long long sv = kScanPrefix; // lanes in front of chunk 0: a prefix of 0
+        if (j >= 0)
+        {
+            sv = ld_status(status + j);
+            while ((sv >> 62) == 0)
+            {
+                __nanosleep(20);
+                sv = ld_status(status + j);
+            }
+        }
+        const unsigned has_prefix = __ballot_sync(kFull, (sv >> 62) == 2);
+        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31; // nearest predecessor with a prefix
+        long long v = (lane <= stop) ? (long long)(sv & kScanValueMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v += __shfl_xor_sync(kFull, v, o);
+        excl += v;
+        if (has_prefix)
+            break;
+        idx -= 32;
+    }
+    if (lane == 0 && chunk != 0)
+    {
+        __threadfence();
+        st_status(status + chunk, kScanPrefix | (unsigned long long)(excl + aggregate));
+    }
+    return excl;
+}
+
+// ctrl[0] = chunk ticket counter (zeroed with the scalars); status[nchunks] zeroed likewise;
+// flags[] holds the row-start bits on entry and the complete tile-start flags on exit.
+__global__ void __launch_bounds__(kMaskThreads)
+    k_mask_build(const int *__restrict__ Bc, long long nnz, long long nwords, unsigned *flags,
+                 int *__restrict__ wordprefix, int *__restrict__ tilecol, unsigned *__restrict__ tilemask,
+                 unsigned *__restrict__ ctrl, unsigned long long *__restrict__ status, int nchunks,
+                 long long *__restrict__ total64)
+{
+    pdl_prologue();
+    constexpr int WPW = kMaskWordsPerWarp, NW = kMaskThreads / 32;
+    __shared__ int sh_chunk;
+    __shared__ int sh_warp[NW];
+    __shared__ long long sh_base;
+    if (threadIdx.x == 0)
+        sh_chunk = (int)atomicAdd(ctrl, 1u);
+    __syncthreads();
+    const int chunk = sh_chunk;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const long long w0 = (long long)chunk * kMaskChunkWords + (long long)warp * WPW; // first word of this warp
+    // columns of the warp's WPW words plus one look-ahead word, all loads issued up front
+    int c[WPW + 1];
+#pragma unroll
+    for (int i = 0; i <= WPW; ++i)
+    {
+        const long long j = (w0 + i) * 32 + lane;
+        c[i] = (j < nnz) ? __ldg(&Bc[j]) : -1;
+    }
+    int prev_last = -1; // column in front of the warp's first nonzero
+    {
+        const long long j = w0 * 32 - 1;
+        if (j >= 0 && j < nnz)
+            prev_last = __ldg(&Bc[j]);
+    }
+    unsigned rowbits[WPW + 1];
+#pragma unroll
+    for (int i = 0; i <= WPW; ++i)
+        rowbits[i] = (w0 + i < nwords) ? flags[w0 + i] : 0u; // row starts (or already-complete flags: a superset)
+    // tile-start flags: the tile column changes, or a row starts
+    unsigned f[WPW + 1];
+    int tiles = 0;
+#pragma unroll
+    for (int i = 0; i <= WPW; ++i)
+    {
+        int p = __shfl_up_sync(kFull, c[i], 1);
+        const int carry = (i == 0) ? prev_last : __shfl_sync(kFull, c[i - 1], 31);
+        if (lane == 0)
+            p = carry;
+        const bool valid = c[i] >= 0;
+        const bool start = valid && (p < 0 || (c[i] >> MHB_TILE_SHIFT) != (p >> MHB_TILE_SHIFT));
+        f[i] = __ballot_sync(kFull, start) | rowbits[i];
+        if (i < WPW)
+            tiles += __popc(f[i]);
+    }
+    // chunk aggregate -> look-back -> tile index in front of every word
+    if (lane == 0)
+        sh_warp[warp] = tiles;
+    __syncthreads();
+    if (warp == 0)
+    {
+        int agg = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            agg += sh_warp[w];
+        const long long excl = chained_scan_lookback(status, chunk, agg);
+        if (lane == 0)
+        {
+            sh_base = excl;
+            if (chunk == nchunks - 1)
+                *total64 = excl + agg;
+        }
+    }
+    __syncthreads();
+    long long run = sh_base;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (w < warp)
+            run += sh_warp[w];
+#pragma unroll
+    for (int i = 0; i < WPW; ++i)
+    {
+        const long long word = w0 + i;
+        if (word >= nwords)
+            break;
+        const unsigned fi = f[i];
+        if (lane == 0)
+        {
+            flags[word] = fi;
+            wordprefix[word] = (int)run;
+        }
+        // mask of every run that STARTS in this word: segmented suffix-OR inside the word ...
+        const bool valid = c[i] >= 0;
+        unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
+        const unsigned above = (lane == 31) ? 0u : (fi >> (lane + 1));
+        const int seg_end = above ? lane + __ffs(above) - 1 : 31; // last lane of this lane's run inside the word
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned v = __shfl_down_sync(kFull, bits, d);
+            if (lane + d <= seg_end)
+                bits |= v;
+        }
+        // ... plus the run's continuation in the leading lanes of the next word
+        const unsigned fn = f[i + 1];
+        const int lead = fn ? __ffs(fn) - 1 : 32;
+        const unsigned ext = __reduce_or_sync(kFull, (lane < lead && c[i + 1] >= 0) ? (1u << (c[i + 1] & 31)) : 0u);
+        if (valid && ((fi >> lane) & 1u))
+        {
+            const int t = (int)run + __popc(fi & lanemask_lt());
+            tilecol[t] = c[i] >> MHB_TILE_SHIFT;
+            tilemask[t] = (seg_end == 31) ? (bits | ext) : bits;
+        }
+        run += __popc(fi);
+    }
+}
+
+// Tile offsets, the per-row descriptor {nnz, tiles, first col, last col} and the twin flag
+// (same tile list as the previous row) of every row of B, one thread per row.
+__global__ void __launch_bounds__(256) k_mask_rows(int K, long long nnz, const int *__restrict__ Bp,
+                                                   const int *__restrict__ Bc, const unsigned *__restrict__ flags,
+                                                   const int *__restrict__ wordprefix,
+                                                   const long long *__restrict__ total64,
+                                                   const int *__restrict__ tilecol,
+                                                   const unsigned *__restrict__ tilemask,
+                                                   int *__restrict__ tileptr, int4 *__restrict__ binfo,
+                                                   unsigned char *__restrict__ same)
+{
+    pdl_prologue();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > K)
+        return;
+    const int total = (int)*total64;
+    if (k == K)
+    {
+        tileptr[K] = total;
+        return;
+    }
+    const int s = __ldg(&Bp[k]), e = __ldg(&Bp[k + 1]);
+    const int ts = tiles_before(s, nnz, flags, wordprefix, total);
+    const int te = tiles_before(e, nnz, flags, wordprefix, total);
+    tileptr[k] = ts;
+    int first = INT_MAX, last = -1;
+    if (e > s)
+    {
+        first = __ldg(&Bc[s]);
+        last = __ldg(&Bc[e - 1]);
+    }
+    binfo[k] = make_int4(e - s, te - ts, first, last);
+    unsigned char r = 0;
+    if (k > 0 && e > s)
+    {
+        const int ps = __ldg(&Bp[k - 1]);
+        if (s - ps == e - s && __ldg(&Bc[ps]) == first && __ldg(&Bc[s - 1]) == last)
+        {
+            const int pts = tiles_before(ps, nnz, flags, wordprefix, total);
+            if (ts - pts == te - ts)
+            {
+                r = 1;
+                for (int t = 0; t < te - ts; ++t)
+                    if (tilecol[pts + t] != tilecol[ts + t] || tilemask[pts + t] != tilemask[ts + t])
+                    {
+                        r = 0;
+                        break;
+                    }
+            }
+        }
+    }
+    same[k] = r;
+}
+
 // same[k] = 1 when row k of B has exactly the column pattern of row k-1 (equal tile lists).
 // Typical of multi-dof FEM matrices, where the rows of one node share their pattern.  The
 // symbolic pass skips such a row when it directly follows its twin in a row of A (OR is

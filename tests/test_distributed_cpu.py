@@ -1,7 +1,10 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: row partition balanced by
-intermediate products, the packed-B broadcast, slice offsets by all-gather, and the
-concatenation by row_ptr offset.  The per-rank SpGEMM is the oracle here (the CUDA path
-cannot run without a GPU); the -m gpu suite runs the same flow on devices."""
+"""World-size-2 gloo tests (CPU) of the multi-GPU HOST logic only: row partition balanced by
+intermediate products, the packed-B broadcast, slice offsets by all-gather, the range-exchange
+plan, and the concatenation by row_ptr offset.  The per-rank multiply is the oracle here -- the
+CUDA path cannot run without a GPU, so these tests say nothing about the kernels or about the
+peer-window exchange.  The CUDA multi-rank path (mhb_shard_*, one process per rank, every slice
+against the oracle) is tests/test_gpu_parity.py::test_row_sharded_spgemm_multi_rank, and
+bench.py checks the slices of every rank at every N (its "parity" field)."""
 import os
 import socket
 

@@ -523,8 +523,8 @@ def test_hash_probe_counter(orc):
     assert np.array_equal(C0.col, C1.col)
     assert st["hash_probes"] > 0 and st["sym_hash_probes"] > 0
     assert st["hash_probes"] < 4 * st["intprod"]  # fill <= 5/8 with linear probing: a few probes per product
-    C2 = t.spgemm_host(A, A)  # the counter restarts with every call
-    assert t.stats["hash_probes"] == st["hash_probes"] or abs(t.stats["hash_probes"] - st["hash_probes"]) < st["hash_probes"]
+    t.spgemm_host(A, A)  # the counter restarts with every call (CAS order may move it a little)
+    assert 0 < t.stats["hash_probes"] < 2 * st["hash_probes"]
     t.set_option("force_sym_path", 1)
     t.set_option("force_num_path", 1)
     F = G.fem3d(4, 4, 10, 3, seed=5)
@@ -578,3 +578,25 @@ def test_suite_large_analog(tool, name):
     got = np.add.reduceat(np.append(C.val, 0.0), np.minimum(C.ptr[:-1], C.nnz))
     got[np.diff(C.ptr) == 0] = 0.0
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-9)
+
+
+def _free_port():
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_spgemm_multi_rank(world):
+    """The multi-GPU path behind the C ABI (mhb_shard_*), one PROCESS per rank: B row-sharded,
+    peer-mapped windows over CUDA IPC, one-sided halo pull and slice sizes, three steps with
+    changing values, the sliced (int32-overflow) form -- every rank's slice of C bit-exact on
+    structure and to 1e-12 on values against the host oracle, slice offsets equal to the
+    oracle's global row_ptr.  Ranks share a device when the box has fewer GPUs than ranks."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "shard_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    ok = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARD-OK")]
+    assert p.returncode == 0 and len(ok) == 5 * world, p.stdout[-3000:] + p.stderr[-3000:]
