@@ -117,6 +117,10 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def mark(self):
+        """Forget what was sampled so far (warm-up); keep sampling."""
+        self.samples, self.reasons = [], set()
+
     def stop(self) -> dict:
         if self.t is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
@@ -156,13 +160,14 @@ def cpu_baseline(A: CSR, B: CSR, intprod: int, budget_s: float = 12.0) -> dict:
 
 
 # ---------------------------------------------------------------------------------------
-L2_NOTE = "flushed between timed steps (256 MiB write)"
+L2_NOTE = "flushed between timed steps (256 MiB written, then read back)"
 
 # numeric bin -> the kernel that serves it (csrc/mhb_capi.cu launch_numeric_bins)
 NUM_KERNEL = {"WIN_COMPACT": "k_num_compact_rowtwins", "WIN_WARP": "k_num_win_group<32>", "WIN_G8": "k_num_win_group<8>",
               "WIN_BLOCK_S": "k_num_win_block", "WIN_BLOCK_L": "k_num_win_block", "H_G8": "k_num_hash_group<8>",
               "H_WARP_XS": "k_num_hash_list<wrows>", "H_WARP_S": "k_num_hash_list<wrows>", "H_WARP_M": "k_num_hash_list",
-              "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_L": "k_num_hash_block",
+              "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_M": "k_num_hash_list",
+              "H_BLOCK_L": "k_num_hash_block",
               "H_GLOBAL": "k_num_hash_block(pool)", "TINY": "k_num_tiny"}
 
 
@@ -179,7 +184,7 @@ def captured_traffic(workload: str, world: int):
     return int(rec["traffic"]), {k: rec[k] for k in ("kernel", "capture") if k in rec}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out_stream=sys.stdout):
     """--impl reference: the reference's own kernels (oracle/_ref) on the SAME matrix our arm
     multiplies at this N (the reference is single-GPU: rank 0 runs the whole N x matrix)."""
     if rank != 0:
@@ -232,7 +237,7 @@ def run_reference(args, rank):
                     config=dict(cfg, intprod=intprod, nnzC=nnzC),
                     e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     gpu_launches=0)
-    print(json.dumps(base), flush=True)
+    print(json.dumps(base), file=out_stream, flush=True)
 
 
 # ---------------------------------------------------------------------------------------
@@ -354,11 +359,16 @@ def main():
                          "round-1 path, grouped NCCL send/recv driven by torch.distributed")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # ONE JSON line on stdout: native libraries (NCCL prints its version banner on fd 1 when
+    # NCCL_DEBUG is set in the environment) are pointed at stderr for the rest of the run
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -390,6 +400,7 @@ def main():
     a_ptr, a_col, a_val = (torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
                            torch.from_numpy(Ablk.val).to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
     # rows of this rank cut into slices of < 2^31 products (local int32 row_ptr per slice, int64 offsets)
     slices = [(a - r0, b - r0) for a, b in slice_rows_fast(work, r0, r1, cap=(1 << 31) - 1)] if r1 > r0 else [(0, 0)]
     mode = "single" if world == 1 else args.exchange
@@ -424,11 +435,24 @@ def main():
         val_own.upload(Bown.val)
         k0, k1, _, exch_bytes = sh.image()
 
+        trace = []  # MHB_BENCH_TRACE=1: device time of exchange / multiply / size post per step
+
         def one_step():
+            tr = os.environ.get("MHB_BENCH_TRACE") == "1"
+            if tr:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                e[0].record(stream)
             sh.exchange()
+            if tr:
+                e[1].record(stream)
             last, total = multiply(lambda s0, s1, cp: sh.symbolic(s0, s1, cp),
                                    lambda cc, cv: sh.numeric_into(a_val, cc, cv))
+            if tr:
+                e[2].record(stream)
             sh.post_size(total)
+            if tr:
+                e[3].record(stream)
+                trace.append(e)
             return last, total
     elif mode == "broadcast":
         sh = Shard(tool, rank, world, B.M, B.N, np.float64, bounds)
@@ -477,6 +501,11 @@ def main():
         off, tot = sizes.offsets()
         return off, tot, None
 
+    # NVML is initialised (and its first, slow queries made) BEFORE anything is timed: r2e showed
+    # the first timed step of the OTHER rank taking 37 ms while rank 0 sat in nvmlInit
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # the very first call is timed too: cold workspace (allocations), cold caches, module load
     cold0, cold1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cold0.record(stream)
@@ -490,14 +519,17 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()  # samples from here on belong to the timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     num_ms, launches = [], 0
     torch.cuda.synchronize()
     for k in range(args.steps):
-        flush.fill_(k & 0xFF)  # evict L2 between timed iterations (outside the event pair)
+        # evict L2 between timed iterations (outside the event pair): write 256 MiB, then read it
+        # back so that L2 is left full of CLEAN lines -- after a write-only flush the step also
+        # pays for draining ~126 MB of dirty lines (r2e: 0.05 ms in front of the first kernel)
+        flush.fill_(k & 0xFF)
+        flush_sink.copy_(flush.view(torch.int64).sum())
         if mode == "peer":
             sh.barrier()       # ranks leave the flush together: no start-time skew inside the event pair
         ev[k][0].record(stream)
@@ -511,7 +543,22 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
     own_ms = float(step_ms.mean().item())
+    per_rank = None
     if world > 1:
+        allsteps = [torch.zeros_like(step_ms) for _ in range(world)]
+        dist.all_gather(allsteps, step_ms)
+        tmg = tool.timing
+        info = torch.tensor([float(Ablk.M), float(Ablk.nnz), float(work[r0:r1].sum()), float(nnz_local),
+                             tmg.total, tmg.Numeric, tmg.Calculate_C_nnz, tmg.Form_mask_matrix_B],
+                            dtype=torch.float64, device=dev)
+        allinfo = [torch.zeros_like(info) for _ in range(world)]
+        dist.all_gather(allinfo, info)
+        per_rank = [{"mean_ms": round(float(t.mean().item()), 4), "median_ms": round(float(t.median().item()), 4),
+                     "max_ms": round(float(t.max().item()), 4), "rows": int(i[0].item()), "nnzA": int(i[1].item()),
+                     "products": int(i[2].item()), "nnzC": int(i[3].item()),
+                     "stage_total_ms": round(float(i[4].item()), 4), "numeric_ms": round(float(i[5].item()), 4),
+                     "symbolic_ms": round(float(i[6].item()), 4), "mask_ms": round(float(i[7].item()), 4),
+                     "steps_ms": [round(float(x), 3) for x in t.tolist()]} for t, i in zip(allsteps, allinfo)]
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)  # max over ranks, per step
     step_ms = step_ms.cpu().numpy()
     ms = float(step_ms.mean())
@@ -555,7 +602,7 @@ def main():
                       "slice_sizes_ok": bool(sizes_ok)}
         if not (all(oks) and sizes_ok):
             if rank == 0:
-                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+                print(json.dumps({"error": "parity check failed", "parity": parity}), file=real_stdout, flush=True)
             raise SystemExit(3)
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside) ----
@@ -625,7 +672,10 @@ def main():
             "parity": parity,
             "gpu_launches": launches, "clocks": clocks,
             "stage_ms": {k: round(v, 4) for k, v in timing.items()},
-            "rank0_ms_per_step": round(own_ms, 4),
+            "rank0_ms_per_step": round(own_ms, 4), "per_rank": per_rank,
+            "rank0_phase_ms": (None if not (mode == "peer" and trace) else
+                               {n: round(float(np.median([t[i].elapsed_time(t[i + 1]) for t in trace[-args.steps:]])), 4)
+                                for i, n in enumerate(("exchange", "symbolic+alloc+numeric", "post_size"))}),
             # the reference's own total leaves the mask build out (src/Timing.cpp:39-42)
             "ms_per_step_reference_convention": round(ms - timing.get("Form_mask_matrix_B", 0.0), 4),
             "cold_first_call_ms": round(cold_ms, 3),
@@ -636,7 +686,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(A, B, intprod)
         if world == 1 and args.workload == "F" and not args.no_suite:
             line["suite"] = suite_breadth(tool)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if sh is not None:
         torch.cuda.synchronize()
         if world > 1:

@@ -210,8 +210,17 @@ int mhb_shard_import(mhb_shard_t s, int phase, const void *blobs /* world * MHB_
  * image the SpGEMM reads: rows [*k0, *k1) of B, *nnz_image entries. */
 int mhb_shard_own_B(mhb_shard_t s, int **dB_col_own, void **dB_val_own, long long *nnz_own);
 int mhb_shard_image(mhb_shard_t s, int *k0, int *k1, long long *nnz_image, long long *halo_bytes_per_step);
-/* The exchange step (stream-ordered on the handle's stream, returns without synchronising). */
+/* The exchange step (stream-ordered on the handle's stream, returns without synchronising):
+ * mhb_shard_exchange = mhb_shard_publish ("my shard of B is final for this step": one flag store
+ * per peer) + mhb_shard_pull (wait for the owners' flags, copy their pieces into the image).
+ * The pull kernel SPINS until the owners have published, so the ranks' kernels must be able to
+ * run at the same time: one GPU per rank.  Ranks that share one GPU (tests on a single-GPU box)
+ * call the two halves separately with a HOST barrier in between, so that no kernel ever waits
+ * for a kernel of another process on the same device; likewise they replace mhb_shard_barrier by
+ * a host barrier and synchronise before mhb_shard_offsets. */
 int mhb_shard_exchange(mhb_shard_t s);
+int mhb_shard_publish(mhb_shard_t s);
+int mhb_shard_pull(mhb_shard_t s);
 /* Device-side barrier over all ranks (peer flags, stream-ordered): call between the end of a
  * step and the next modification of B's shard, and to align ranks before timing. */
 int mhb_shard_barrier(mhb_shard_t s);

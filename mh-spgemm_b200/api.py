@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
 SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -36,7 +36,8 @@ ABI_SYMBOLS = [
     "mhb_form_mask_matrix_B", "mhb_get_row_info", "mhb_get_bins", "mhb_get_timing", "mhb_get_stats",
     "mhb_transpose_f64", "mhb_transpose_f32", "mhb_get_stream",
     "mhb_shard_create", "mhb_shard_destroy", "mhb_shard_last_error", "mhb_shard_set_A", "mhb_shard_export",
-    "mhb_shard_import", "mhb_shard_own_B", "mhb_shard_image", "mhb_shard_exchange", "mhb_shard_barrier",
+    "mhb_shard_import", "mhb_shard_own_B", "mhb_shard_image", "mhb_shard_exchange", "mhb_shard_publish",
+    "mhb_shard_pull", "mhb_shard_barrier",
     "mhb_shard_symbolic", "mhb_shard_numeric_f64", "mhb_shard_numeric_f32", "mhb_shard_post_size",
     "mhb_shard_offsets", "mhb_nccl_unique_id", "mhb_shard_init_nccl", "mhb_shard_broadcast",
 ]
@@ -112,6 +113,8 @@ def load_library() -> C.CDLL:
     L.mhb_shard_own_B.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
     L.mhb_shard_image.argtypes = [vp, C.POINTER(ip), C.POINTER(ip), C.POINTER(ll), C.POINTER(ll)]
     L.mhb_shard_exchange.argtypes = [vp]
+    L.mhb_shard_publish.argtypes = [vp]
+    L.mhb_shard_pull.argtypes = [vp]
     L.mhb_shard_barrier.argtypes = [vp]
     L.mhb_shard_symbolic.argtypes = [vp, ip, ip, vp, C.POINTER(ll)]
     L.mhb_shard_numeric_f64.argtypes = [vp, vp, vp, vp]

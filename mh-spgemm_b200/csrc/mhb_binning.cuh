@@ -16,6 +16,18 @@
 namespace mhb
 {
 
+// Zero `n16` 16-byte words (the per-call scalar / ticket / status / flag block).  A kernel, not
+// cudaMemsetAsync: the driver's memset of this 0.05-0.5 MB block measured 50 us on the stream
+// (r2c: mem_alloc 0.005 -> 0.057 ms), a grid-stride store loop takes 2-3 us and chains with
+// programmatic dependent launch like the rest of the pipeline.
+__global__ void __launch_bounds__(256) k_zero16(uint4 *__restrict__ p, long long n16)
+{
+    pdl_prologue();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---------------------------------------------------------------------------------------
 // Exclusive scan of n ints (n up to 2^31) in two launches: block sums, then scan + apply.
 // ---------------------------------------------------------------------------------------

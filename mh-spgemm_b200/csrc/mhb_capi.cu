@@ -317,7 +317,10 @@ constexpr size_t kStatusOffset = kCtrlOffset + 64;      // unsigned long long st
 inline long long mask_words(long long nnz) { return (nnz + 31) / 32; }
 inline int mask_chunks(long long nnz) { return (int)((mask_words(nnz) + kMaskChunkWords - 1) / kMaskChunkWords); }
 inline size_t flags_offset(long long nnz) { return kStatusOffset + (size_t)(mask_chunks(nnz) + 1) * 8; }
-inline size_t scal_bytes(long long nnz) { return flags_offset(nnz) + (size_t)(mask_words(nnz) + 2) * 4; }
+inline size_t scal_bytes(long long nnz) { return (flags_offset(nnz) + (size_t)(mask_words(nnz) + 2) * 4 + 15) / 16 * 16; }
+
+// zero the first `bytes` (a multiple of 16) of the scalar block on the handle's stream
+int zero_scal(mhb_context *h, size_t bytes);
 
 int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
 {
@@ -349,6 +352,14 @@ int ensure_workspace(mhb_context *h, int M, int K, int nnzB, bool *grew)
         *grew |= r.b->grew;
     }
     CU(h->h_scal.ensure(SC_COUNT * 4));
+    return MHB_OK;
+}
+
+int zero_scal(mhb_context *h, size_t bytes)
+{
+    const long long n16 = (long long)(bytes / 16);
+    LAUNCH(h, k_zero16, (int)std::min<long long>(std::max<long long>(cdiv(n16, 256), 1), h->num_sms * 8), 256, 0,
+           h->scal.as<uint4>(), n16);
     return MHB_OK;
 }
 
@@ -476,7 +487,7 @@ int launch_symbolic_bins(mhb_context *h)
         constexpr int G = 32, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_WARP_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_WARP)) > 0)
@@ -492,7 +503,7 @@ int launch_symbolic_bins(mhb_context *h)
         constexpr int G = 8, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, counts,
+               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_G8_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_G8)) > 0)
@@ -591,6 +602,18 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
                bins + off[NB_WIN_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+    }
+    if ((n = n_of(NB_H_BLOCK_M)) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        if (h->claim_list)
+        {
+            if (int e_ = launch_hash_list(NB_H_BLOCK_M, NB_H_BLOCK_M_SLOTS, 512, cap_blocks)) return e_;
+        }
+        else
+            LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
+                      bins + off[NB_H_BLOCK_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      log2_ceil(NB_H_BLOCK_L_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_H_BLOCK_S)) > 0)
     {
@@ -739,8 +762,8 @@ int set_kernel_attributes(mhb_context *h)
     CU(allow_smem(k_num_win_group<32, double>, 8 * (NB_WIN_WARP_COLS * 8 + 544)));
     CU(allow_smem(k_num_win_group<8, float>, 32 * (NB_WIN_G8_COLS * 4 + 160)));
     CU(allow_smem(k_num_win_group<32, float>, 8 * (NB_WIN_WARP_COLS * 4 + 544)));
-    CU(allow_smem(k_num_hash_list<double, false>, (int)hash_list_smem<double>(NB_H_BLOCK_S_SLOTS)));
-    CU(allow_smem(k_num_hash_list<float, false>, (int)hash_list_smem<float>(NB_H_BLOCK_S_SLOTS)));
+    CU(allow_smem(k_num_hash_list<double, false>, (int)hash_list_smem<double>(NB_H_BLOCK_M_SLOTS)));
+    CU(allow_smem(k_num_hash_list<float, false>, (int)hash_list_smem<float>(NB_H_BLOCK_M_SLOTS)));
     CU(allow_smem(k_num_tiny<double>, NB_TINY_MAX * kTinyRowThreads * 12));
     CU(allow_smem(k_num_tiny<float>, NB_TINY_MAX * kTinyRowThreads * 8));
     CU(allow_smem(k_num_compact_rowtwins<double>, 4 * 3 * (NB_WIN_COMPACT_MAXN + 34) * 8 + 4 * 100 * 8));
@@ -789,7 +812,9 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
         return rc;
     int *scal = h->scal.as<int>();
     int *hs = h->h_scal.as<int>();
-    CU(cudaMemsetAsync(scal, 0, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4, h->stream));
+    rc = zero_scal(h, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4);
+    if (rc)
+        return rc;
     CU(cudaEventRecord(h->ev[EV_ALLOC], h->stream));
     // twin rows of A (same column list as the previous row): B's flags when A is B; otherwise
     // compared now on a helper stream, hidden behind the mask build that only needs B
@@ -1384,7 +1409,9 @@ extern "C"
         int rc = ensure_workspace(h, 0, K, nnzB, &grew);
         if (rc)
             return rc;
-        CU(cudaMemsetAsync(h->scal.p, 0, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4, h->stream));
+        rc = zero_scal(h, h->mask_onepass ? scal_bytes(nnzB) : (size_t)SC_COUNT * 4);
+        if (rc)
+            return rc;
         rc = build_mask_matrix(h, K, nnzB, dB_ptr, dB_col);
         if (rc)
             return rc;

@@ -64,6 +64,7 @@ enum MhbNumBin
     NB_H_WARP_M,    // hash, warp/row,    n <= 320 (512 slots)
     NB_WIN_COMPACT, // window rows with a stored symbolic bitmap, n <= 448: rank-mapped accumulators,
                     // up to three twin rows of A per warp
+    NB_H_BLOCK_M,   // hash, block/row,   n <= 5120 (8192 slots, claim list)
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -82,6 +83,8 @@ enum MhbNumBin
 #define NB_H_WARP_L_MAX 640
 #define NB_H_BLOCK_S_SLOTS 4096
 #define NB_H_BLOCK_S_MAX 2560
+#define NB_H_BLOCK_M_SLOTS 8192
+#define NB_H_BLOCK_M_MAX 5120
 #define NB_H_BLOCK_L_SLOTS 16384
 #define NB_H_BLOCK_L_MAX 10240
 #define NB_WIN_COMPACT_MAXN 448
@@ -168,6 +171,8 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf
         return NB_H_WARP_L;
     if (n <= NB_H_BLOCK_S_MAX)
         return NB_H_BLOCK_S;
+    if (n <= NB_H_BLOCK_M_MAX)
+        return NB_H_BLOCK_M;
     if (n <= NB_H_BLOCK_L_MAX)
         return NB_H_BLOCK_L;
     return NB_H_GLOBAL;

@@ -174,20 +174,26 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 
 // Exclusive prefix of chunk `chunk` (sum of the aggregates of all chunks in front of it), by
-// one warp: 32 predecessors per round, newest first; stops at the first one that already
-// knows its inclusive prefix.  Publishes this chunk's aggregate first and its inclusive
-// prefix last.  Returns the exclusive prefix in every lane.
-__device__ __forceinline__ long long chained_scan_lookback(unsigned long long *status, int chunk, long long aggregate)
+// the WHOLE block: 256 predecessors per round, newest first (thread t looks at chunk - 1 - t);
+// stops at the nearest one that already knows its inclusive prefix.  Publishes this chunk's
+// aggregate first and its inclusive prefix last.  All chunks of a wave publish their aggregates
+// at about the same time, so the depth of the walk is what costs: a one-warp window needed
+// chunk/32 rounds of L2 latency (44 us for 2 070 chunks, r2f launch list); 256-wide it is 8x
+// shallower.  Must be called by all threads of the block; returns the exclusive prefix.
+// sh: NW + 2 long long of shared memory.
+template <int NW>
+__device__ __forceinline__ long long chained_scan_lookback(unsigned long long *status, int chunk, long long aggregate,
+                                                           long long *sh)
 {
-    const int lane = lane_id();
-    if (lane == 0)
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
         st_status(status + chunk, (chunk == 0 ? kScanPrefix : kScanAggregate) | (unsigned long long)aggregate);
     long long excl = 0;
     int idx = chunk - 1;
     while (idx >= 0)
     {
-        const int j = idx - lane;
-        unsigned long long sv = kScanPrefix; // lanes in front of chunk 0: a prefix of 0
+        const int j = idx - (int)threadIdx.x;
+        unsigned long long sv = kScanPrefix; // in front of chunk 0: a prefix of 0
         if (j >= 0)
         {
             sv = ld_status(status + j);
@@ -198,17 +204,31 @@ __device__ __forceinline__ long long chained_scan_lookback(unsigned long long *s
             }
         }
         const unsigned has_prefix = __ballot_sync(kFull, (sv >> 62) == 2);
-        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31; // nearest predecessor with a prefix
+        const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31; // nearest predecessor with a prefix in this warp's window
         long long v = (lane <= stop) ? (long long)(sv & kScanValueMask) : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
             v += __shfl_xor_sync(kFull, v, o);
-        excl += v;
-        if (has_prefix)
+        if (lane == 0)
+            sh[warp] = has_prefix ? -v - 1 : v; // negative: this window ends the walk
+        __syncthreads();
+        bool done = false;
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+        {
+            const long long x = sh[w];
+            if (!done)
+            {
+                excl += (x < 0) ? -(x + 1) : x;
+                done = x < 0;
+            }
+        }
+        __syncthreads();
+        if (done)
             break;
-        idx -= 32;
+        idx -= NW * 32;
     }
-    if (lane == 0 && chunk != 0)
+    if (threadIdx.x == 0 && chunk != 0)
     {
         __threadfence();
         st_status(status + chunk, kScanPrefix | (unsigned long long)(excl + aggregate));
@@ -228,7 +248,7 @@ __global__ void __launch_bounds__(kMaskThreads)
     constexpr int WPW = kMaskWordsPerWarp, NW = kMaskThreads / 32;
     __shared__ int sh_chunk;
     __shared__ int sh_warp[NW];
-    __shared__ long long sh_base;
+    __shared__ long long sh_look[NW + 2];
     if (threadIdx.x == 0)
         sh_chunk = (int)atomicAdd(ctrl, 1u);
     __syncthreads();
@@ -273,22 +293,14 @@ __global__ void __launch_bounds__(kMaskThreads)
     if (lane == 0)
         sh_warp[warp] = tiles;
     __syncthreads();
-    if (warp == 0)
-    {
-        int agg = 0;
+    int agg = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w)
-            agg += sh_warp[w];
-        const long long excl = chained_scan_lookback(status, chunk, agg);
-        if (lane == 0)
-        {
-            sh_base = excl;
-            if (chunk == nchunks - 1)
-                *total64 = excl + agg;
-        }
-    }
-    __syncthreads();
-    long long run = sh_base;
+    for (int w = 0; w < NW; ++w)
+        agg += sh_warp[w];
+    const long long excl = chained_scan_lookback<NW>(status, chunk, agg, sh_look);
+    if (threadIdx.x == 0 && chunk == nchunks - 1)
+        *total64 = excl + agg;
+    long long run = excl;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
         if (w < warp)

@@ -607,16 +607,20 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_tot /*32*/, int 
     if (lane_id() == 31)
         warp_tot[threadIdx.x >> 5] = incl;
     __syncthreads();
+    // every warp scans the (at most 32) warp totals itself: ten shuffles instead of a serial
+    // loop over the warps in every thread
     const int nw = blockDim.x >> 5;
-    int pre = 0, tot = 0;
-    for (int w = 0; w < nw; ++w)
+    const int wt = lane_id() < nw ? warp_tot[lane_id()] : 0;
+    int wi = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-        int t = warp_tot[w];
-        if (w < (int)(threadIdx.x >> 5))
-            pre += t;
-        tot += t;
+        int t = __shfl_up_sync(kFull, wi, o);
+        if (lane_id() >= o)
+            wi += t;
     }
-    *total = tot;
+    const int pre = __shfl_sync(kFull, wi - wt, threadIdx.x >> 5);
+    *total = __shfl_sync(kFull, wi, 31);
     return pre + incl - v;
 }
 
@@ -1109,6 +1113,12 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
         }
         else
         {
+            // the table of this row: smallest power of two >= 2 n (>= 1 024), at most the bin's;
+            // initialisation, compaction sweep and sort scratch then scale with the row
+            int lrow = 10;
+            while ((1 << lrow) < 2 * n_row)
+                ++lrow;
+            logS = min(logS_fixed, lrow);
             vals = reinterpret_cast<T *>(sm_raw);
             keys = reinterpret_cast<int *>(vals + ((size_t)1 << logS));
         }
@@ -1213,11 +1223,11 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
     int np = 0;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
-    const int S = 1 << logS, NB = S >> 2, nmax = (S >> 3) * 5;
+    const int S = 1 << logS, NBmax = S >> 2, nmax = (S >> 3) * 5;
     T *vals = reinterpret_cast<T *>(sm_raw + (WROWS ? (size_t)(threadIdx.x >> 5) * table_bytes : 0));
     int *keys = reinterpret_cast<int *>(vals + S);
-    int *start = keys + S;      // [NB + 1] bucket counts -> bucket begins -> bucket ends
-    int *misc = start + NB + 1; // [0] entries claimed so far
+    int *start = keys + S;         // [NB + 1] bucket counts -> bucket begins -> bucket ends
+    int *misc = start + NBmax + 1; // [0] entries claimed so far
     int *bkey = misc + 3;       // keys in bucket order
     unsigned short *list = reinterpret_cast<unsigned short *>(bkey + nmax);
     unsigned short *idx = list + nmax; // slots in bucket order
@@ -1245,7 +1255,12 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         const int n = __ldg(&Cp[row + 1]) - out;
         const int4 info = __ldg(&arow[row]);
         const int cmin = info.z, W = info.w - info.z + 1;
-        const int sh = max(0, ceil_log2_dev(W) - (logS - 2));
+        // table of THIS row: the smallest power of two with fill <= 5/8 (the shared-memory layout
+        // is that of the bin's largest table; a smaller row uses a prefix of it, so its bucket
+        // arrays, scans and probe cycles are sized by the row, not by the bin)
+        const int lS = min(logS, max(5, ceil_log2_dev((n * 8 + 4) / 5)));
+        const int NB = 1 << (lS - 2);
+        const int sh = max(0, ceil_log2_dev(W) - (lS - 2));
         for (int b = tid; b <= NB; b += nthr)
             start[b] = 0;
         if (tid == 0)
@@ -1257,8 +1272,8 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
             [&](int c, T v, T a) {
                 // find-or-claim, all lanes in lockstep (c < 0: nothing to insert): the loop leaves
                 // when every lane has its slot, so the value update below runs once per step
-                const unsigned S1 = (unsigned)S - 1u;
-                unsigned h = hash_slot((unsigned)c, logS);
+                const unsigned S1 = (1u << lS) - 1u;
+                unsigned h = hash_slot((unsigned)c, lS);
                 int claimed = -1;
                 bool need = c >= 0;
                 for (unsigned it = 0; it <= S1 && __any_sync(kFull, need); ++it)
@@ -1420,7 +1435,7 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
                 Cv[out + i] = vals[i];
             }
             bar();
-            for (int i = tid; i < S; i += nthr) // full clear: slots outside [0, P) may still be set
+            for (int i = tid; i < (1 << lS); i += nthr) // full clear of the row's table: slots outside [0, P) may still be set
             {
                 keys[i] = -1;
                 vals[i] = T(0);

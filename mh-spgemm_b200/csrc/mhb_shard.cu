@@ -626,15 +626,32 @@ extern "C"
         return MHB_OK;
     }
 
-    int mhb_shard_exchange(mhb_shard_t s)
+    int mhb_shard_publish(mhb_shard_t s)
     {
         if (!s || s->phase != 3)
-            return sfail(s, MHB_ERR_ARG, "mhb_shard_exchange before the plan is complete");
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_publish before the plan is complete");
+        if (s->world == 1)
+            return MHB_OK;
+        ++s->pub_epoch;
+        k_shard_publish<<<1, 32, 0, stream_of(s)>>>(s->pm, s->world, s->rank, s->pub_epoch);
+        SCU(cudaGetLastError());
+        return MHB_OK;
+    }
+
+    int mhb_shard_exchange(mhb_shard_t s)
+    {
+        if (int rc = mhb_shard_publish(s))
+            return rc;
+        return mhb_shard_pull(s);
+    }
+
+    int mhb_shard_pull(mhb_shard_t s)
+    {
+        if (!s || s->phase != 3)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_pull before the plan is complete");
         if (s->world == 1)
             return MHB_OK;
         cudaStream_t st = stream_of(s);
-        ++s->pub_epoch;
-        k_shard_publish<<<1, 32, 0, st>>>(s->pm, s->world, s->rank, s->pub_epoch);
         if (s->plan.npieces > 0)
         {
             long long total = 0;

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kSymThreads)
     k_sym_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const int *__restrict__ tileptr,
                      const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
-                     int *__restrict__ counts, int logS, int *__restrict__ scal,
+                     const int4 *__restrict__ arow, int *__restrict__ counts, int logS, int *__restrict__ scal,
                      unsigned long long *__restrict__ probes)
 {
     extern __shared__ unsigned sm_u[];
@@ -294,12 +294,21 @@ __global__ void __launch_bounds__(kSymThreads)
     int np = 0;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
-    const int S = 1 << logS;
-    int *keys = (int *)sm_u + (size_t)g * 2 * S;
-    unsigned *masks = (unsigned *)(keys + S);
+    const int Smax = 1 << logS;
+    int *keys = (int *)sm_u + (size_t)g * 2 * Smax;
+    unsigned *masks = (unsigned *)(keys + Smax);
     for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
     {
         const int row = rows[r];
+        // table of THIS row: power of two >= 4/3 of its tile upper bound min(tile-flop, spanned
+        // words); initialisation and the popcount sweep then scale with the row, not the bin
+        const int4 info = __ldg(&arow[row]);
+        const int wt = (info.w >> MHB_TILE_SHIFT) - (info.z >> MHB_TILE_SHIFT) + 1;
+        const int ub = min(info.y, wt);
+        int lS = 5;
+        while (lS < logS && (1 << lS) * 3 < ub * 4)
+            ++lS;
+        const int S = 1 << lS;
         for (int w = l; w < S; w += G)
         {
             keys[w] = -1;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(kSymThreads)
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
         walk_flat_post<G, NoVal, unsigned>(
             gm, l, s, e, 0, 1, Ac, (const NoVal *)nullptr, tileptr, tilecol, tilemask,
-            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(gm, keys, masks, logS, tc, m, scal, np); },
+            [&](int tc, unsigned m, NoVal) { return tile_insert_lockstep(gm, keys, masks, lS, tc, m, scal, np); },
             [](int) {});
         __syncwarp(gm);
         int c = 0;
@@ -354,7 +363,15 @@ __global__ void __launch_bounds__(kSymThreads)
             keys = pool + (size_t)blockIdx.x * 2 * pool_slots;
         }
         else
+        {
+            const int4 info = arow[row];
+            const int wt = (info.w >> MHB_TILE_SHIFT) - (info.z >> MHB_TILE_SHIFT) + 1;
+            const int ub = min(info.y, wt);
+            logS = 8; // the row's own table: power of two >= 4/3 ub, at most the bin's
+            while (logS < logS_fixed && (1 << logS) * 3 < ub * 4)
+                ++logS;
             keys = (int *)sm_u;
+        }
         const int S = 1 << logS;
         unsigned *masks = (unsigned *)(keys + S);
         for (int w = threadIdx.x; w < S; w += blockDim.x)

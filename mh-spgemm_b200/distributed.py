@@ -334,6 +334,15 @@ class Shard:
     def exchange(self):
         self._chk(self.L.mhb_shard_exchange(self.s))
 
+    def publish(self):
+        """First half of exchange(): flag stores only, never waits."""
+        self._chk(self.L.mhb_shard_publish(self.s))
+
+    def pull(self):
+        """Second half of exchange(): spins until the owners have published -- ranks that share
+        one GPU must put a host barrier between publish() and pull() (include/mhb_spgemm.h)."""
+        self._chk(self.L.mhb_shard_pull(self.s))
+
     def barrier(self):
         self._chk(self.L.mhb_shard_barrier(self.s))
 

@@ -43,6 +43,29 @@ def main():
     torch.cuda.set_device(dev)
     tool = api.Tool(dev)
     orc = Oracle()
+    # Ranks that share a GPU must never have a kernel of one process spin on a flag that a kernel
+    # of another process writes (the two are not guaranteed to run at the same time; the pool's
+    # profiling guide reports Xid 109 for exactly that).  With fewer GPUs than ranks every wait
+    # is therefore satisfied BEFORE its kernel is launched: stream sync + host barrier.
+    shared = torch.cuda.device_count() < world
+
+    def host_fence():
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def exchange(sh):
+        if shared:
+            sh.publish()
+            host_fence()
+            sh.pull()
+        else:
+            sh.exchange()
+
+    def barrier(sh):
+        if shared:
+            host_fence()
+        else:
+            sh.barrier()
     names = sys.argv[1:] or list(CASES)
     for name in names:
         A = CASES[name]()
@@ -65,13 +88,15 @@ def main():
         for step in range(3):
             scale = 1.0 + step  # B's values change every step: the exchange must deliver the new ones
             val_own.upload(Bown.val * A.val.dtype.type(scale))
-            sh.exchange()
+            exchange(sh)
             dCp = api.DeviceArray(count=Ablk.M + 1, dtype=np.int32)
             nnz = sh.symbolic(0, Ablk.M, dCp)
             dCc = api.DeviceArray(count=max(nnz, 1), dtype=np.int32)
             dCv = api.DeviceArray(count=max(nnz, 1), dtype=A.val.dtype)
             sh.numeric_into(dAv, dCc, dCv)
             sh.post_size(nnz)
+            if shared:
+                host_fence()
             off, tot, sizes = sh.offsets()
             cp, cc, cv = dCp.numpy(), dCc.numpy()[:nnz], dCv.numpy()[:nnz]
             assert np.array_equal(cp.astype(np.int64), Cp), f"{name} rank {rank}: row_ptr differs"
@@ -81,12 +106,12 @@ def main():
             # slice offsets == the oracle's global row_ptr at the block boundaries
             assert off == int(gp[r0]) and tot == int(gp[-1]), (off, tot, int(gp[r0]), int(gp[-1]))
             assert sizes == [int(gp[int(bounds[r + 1])] - gp[int(bounds[r])]) for r in range(world)]
-            sh.barrier()  # nobody may still be pulling when the next step rewrites the shard
+            barrier(sh)  # nobody may still be pulling when the next step rewrites the shard
             for d in (dCp, dCc, dCv):
                 d.free()
         # the rows of a rank cut into two slices after ONE exchange (the int32-overflow path)
         if Ablk.M >= 2:
-            sh.exchange()
+            exchange(sh)
             mid = Ablk.M // 2
             got = []
             for lo, hi in ((0, mid), (mid, Ablk.M)):
@@ -99,8 +124,8 @@ def main():
             from mh_spgemm_b200.distributed import concat_slices
             p2, c2, v2 = concat_slices(got)
             assert np.array_equal(p2, Cp) and np.array_equal(c2, Cc)
-            sh.barrier()
-        tool.L.mhb_memcpy_d2h  # noqa: B018  (keep the library alive until the shard is closed)
+            barrier(sh)
+        torch.cuda.synchronize()
         sh.close()
         print(f"SHARD-OK {name} rank {rank}/{world} dev {dev} rows [{r0},{r1}) image [{k0},{k1}) halo {halo} B nnzC {int(Cp[-1])}",
               flush=True)
