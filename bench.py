@@ -166,7 +166,7 @@ L2_NOTE = "flushed between timed steps (256 MiB written, then read back)"
 NUM_KERNEL = {"WIN_COMPACT": "k_num_compact_rowtwins", "WIN_WARP": "k_num_win_group<32>", "WIN_G8": "k_num_win_group<8>",
               "WIN_BLOCK_S": "k_num_win_block", "WIN_BLOCK_L": "k_num_win_block", "H_G8": "k_num_hash_group<8>",
               "H_WARP_XS": "k_num_hash_list<wrows>", "H_WARP_S": "k_num_hash_list<wrows>", "H_WARP_M": "k_num_hash_list",
-              "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_M": "k_num_hash_list",
+              "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_M": "k_num_hash_list", "H_BLOCK_XS": "k_num_hash_list",
               "H_BLOCK_L": "k_num_hash_block",
               "H_GLOBAL": "k_num_hash_block(pool)", "TINY": "k_num_tiny"}
 

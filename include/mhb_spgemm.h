@@ -51,14 +51,19 @@ typedef struct mhb_stats {
     long long tileflop;      /* same sum over B tile counts (inc/Form_mask_matrix_B.cuh:14-54) */
     long long ntiles_B;      /* tiles in B's mask matrix                                */
     long long nnzC;
-    int sym_bin_size[16];    /* rows per symbolic bin  */
-    int num_bin_size[16];    /* rows per numeric bin   */
+    int sym_bin_size[24];    /* rows per symbolic bin  */
+    int num_bin_size[24];    /* rows per numeric bin   */
     int gpu_launches;        /* kernels launched by the last call */
     /* option "count_probes": probes of the hash kernels that found their slot taken by another
      * key -- the reference's HASH_CONFLICT counter (inc/common.h:18, inc/numeric.cuh:116-118,
      * inc/Calculate_C_nnz.cuh:153); 0 when the option is off */
     long long hash_probes;     /* numeric phase (column hash)  */
     long long sym_hash_probes; /* symbolic phase (tile hash)   */
+    /* symbolic phases on this handle that were launched from the previous call's bin sizes
+     * without the mid-pipeline host read (option "speculate"), and how many of them had to be
+     * re-run the ordinary way because the guess did not cover the input */
+    int speculative_launches;
+    int speculative_misses;
 } mhb_stats;
 
 /* ---- lifetime (replaces Tool::allocate / Tool::release, src/Tool.cu:4-69) ---- */
@@ -72,7 +77,10 @@ int mhb_set_stream(mhb_handle_t h, void *cuda_stream);
  * "nnz_limit" (report MHB_ERR_OVERFLOW above this nnz(C); default INT_MAX), "verbose";
  * kernel selection: "compact_rows" (1), "claim_list" (1), "row_twins" (0), "sym_twins" (1), "pdl" (1:
  * programmatic dependent launch of the main-stream kernel chain; env MHB_PDL overrides at create);
- * "count_probes" (0): count failed hash probes into mhb_stats.hash_probes / sym_hash_probes. */
+ * "count_probes" (0): count failed hash probes into mhb_stats.hash_probes / sym_hash_probes;
+ * "speculate" (1): a call with the shape of the previous one launches its symbolic kernels from
+ * that call's bin sizes (one host read per SpGEMM instead of two; verified, re-run on a miss);
+ * "mask_onepass" (1): one-pass mask builder (0: the round-1 five-kernel chain). */
 int mhb_set_option(mhb_handle_t h, const char *key, long long value);
 
 /* ---- the symbolic-then-numeric contract (MH_spgemm, src/main.cu:12-72) ---- */
@@ -155,7 +163,7 @@ int mhb_form_mask_matrix_B(mhb_handle_t h, int K, int N, int nnzB, const int *dB
  * ascending row order inside a bin; h_bin_offset has nbins+1 entries. */
 int mhb_get_row_info(mhb_handle_t h, const int **d_row_info /* int4 per row */);
 int mhb_get_bins(mhb_handle_t h, int which, int *nbins, const int **d_bins,
-                 int *h_bin_offset /* 17 ints */);
+                 int *h_bin_offset /* 25 ints */);
 
 /* cudaStream_t the handle currently launches on (for callers that order their own work). */
 int mhb_get_stream(mhb_handle_t h, void **cuda_stream);

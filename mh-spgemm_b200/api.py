@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
 SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M", "H_BLOCK_XS"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -60,14 +60,16 @@ class Timing(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("intprod", C.c_longlong), ("tileflop", C.c_longlong), ("ntiles_B", C.c_longlong),
-                ("nnzC", C.c_longlong), ("sym_bin_size", C.c_int * 16), ("num_bin_size", C.c_int * 16),
-                ("gpu_launches", C.c_int), ("hash_probes", C.c_longlong), ("sym_hash_probes", C.c_longlong)]
+                ("nnzC", C.c_longlong), ("sym_bin_size", C.c_int * 24), ("num_bin_size", C.c_int * 24),
+                ("gpu_launches", C.c_int), ("hash_probes", C.c_longlong), ("sym_hash_probes", C.c_longlong),
+                ("speculative_launches", C.c_int), ("speculative_misses", C.c_int)]
 
     def as_dict(self):
         return dict(intprod=self.intprod, tileflop=self.tileflop, ntiles_B=self.ntiles_B, nnzC=self.nnzC,
                     sym_bins=dict(zip(SYM_BINS, list(self.sym_bin_size))),
                     num_bins=dict(zip(NUM_BINS, list(self.num_bin_size))), gpu_launches=self.gpu_launches,
-                    hash_probes=self.hash_probes, sym_hash_probes=self.sym_hash_probes)
+                    hash_probes=self.hash_probes, sym_hash_probes=self.sym_hash_probes,
+                    speculative_launches=self.speculative_launches, speculative_misses=self.speculative_misses)
 
 
 def load_library() -> C.CDLL:
@@ -331,7 +333,7 @@ class Tool:
 
     def bins(self, which: int, M: int):
         nb, p = C.c_int(), C.c_void_p()
-        off = (C.c_int * 17)()
+        off = (C.c_int * 25)()
         self._chk(self.L.mhb_get_bins(self.h, which, C.byref(nb), C.byref(p), off))
         return int(nb.value), _d2h(p.value, M, np.int32), np.array(list(off), np.int32)
 

@@ -126,6 +126,10 @@ struct mhb_context
     const unsigned char *asame = nullptr; // twin flags of A's rows (== bsame when A aliases B)
     int sym_twins = 1;                   // option "sym_twins": symbolic computes one row per run of twin rows of A
     int pdl = 1;                         // option "pdl": programmatic dependent launch of the main-stream chain
+    int speculate = 1;                   // option "speculate": launch the symbolic bins from the previous call's bin sizes (no host read #1)
+    bool spec_ok = false;                // the previous symbolic on this handle finished and left its bin sizes behind
+    int spec_key[5] = {0, 0, 0, 0, 0};   // M, K, N, nnzA, nnzB of that call
+    int spec_calls = 0, spec_misses = 0; // statistics (mhb_stats)
     int mask_onepass = 1;                // option "mask_onepass": one-pass mask builder (0: the round-1 five-kernel chain)
     int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
@@ -423,11 +427,17 @@ int check_dev_error(mhb_context *h, const int *hs)
 }
 
 // ---- family 3 launches ------------------------------------------------------------------
-int launch_symbolic_bins(mhb_context *h)
+// spec: the host has NOT read this call's bin sizes; h->sym_off / h->max_tileflop are those of the
+// previous call on the handle and only size the grids and scratch -- the kernels take their
+// row ranges from the device-side offsets (RowList), and do_symbolic verifies the guess later.
+int launch_symbolic_bins(mhb_context *h, bool spec)
 {
     const int *off = h->sym_off;
     auto n_of = [&](int b) { return off[b + 1] - off[b]; };
     const int *bins = h->bins_sym.as<int>();
+    auto list = [&](int b) {
+        return spec ? RowList{bins, h->scal.as<int>() + SC_SYM_OFF + b, -1} : RowList{bins + off[b], nullptr, n_of(b)};
+    };
     const int *tp = h->tileptr.as<int>();
     const int *tc = h->tilecol.as<int>();
     const unsigned *tm = h->tilemask.as<unsigned>();
@@ -458,28 +468,28 @@ int launch_symbolic_bins(mhb_context *h)
         int nblk = (int)std::min<long long>(std::min(n, h->num_sms * 2), std::max<long long>(1, (1LL << 30) / slice));
         CU(h->pool.ensure(slice * nblk));
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_hash_block, nblk, kSymThreads, 0, bins + off[SB_H_GLOBAL], n, h->Ap, h->Ac, tp, tc, tm,
+        LAUNCH_ON(h, st, k_sym_hash_block, nblk, kSymThreads, 0, list(SB_H_GLOBAL), h->Ap, h->Ac, tp, tc, tm,
                arow, counts, 0, h->pool.as<int>(), slots, scal, probes);
     }
     if ((n = n_of(SB_H_BLOCK_L)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_L_SLOTS * 4,
-               bins + off[SB_H_BLOCK_L], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               list(SB_H_BLOCK_L), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_BLOCK_L_SLOTS), (int *)nullptr, 0LL, scal, probes);
     }
     if ((n = n_of(SB_BM_BLOCK)) > 0)
     {
         int words = std::min<long long>(SB_BM_BLOCK_WORDS, ((long long)h->N + 31) / 32 + 1);
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, bins + off[SB_BM_BLOCK],
-               n, h->Ap, h->Ac, tp, tc, tm, arow, counts);
+        LAUNCH_ON(h, st, k_sym_bitmap_block, std::min(n, cap_blocks), kSymThreads, words * 4, list(SB_BM_BLOCK),
+               h->Ap, h->Ac, tp, tc, tm, arow, counts);
     }
     if ((n = n_of(SB_H_BLOCK_S)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_block, std::min(n, cap_blocks), kSymThreads, 2 * SB_H_BLOCK_S_SLOTS * 4,
-               bins + off[SB_H_BLOCK_S], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               list(SB_H_BLOCK_S), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_BLOCK_S_SLOTS), (int *)nullptr, 0LL, scal, probes);
     }
     if ((n = n_of(SB_H_WARP)) > 0)
@@ -487,7 +497,7 @@ int launch_symbolic_bins(mhb_context *h)
         constexpr int G = 32, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_WARP_SLOTS * 4, bins + off[SB_H_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               GPB * 2 * SB_H_WARP_SLOTS * 4, list(SB_H_WARP), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_WARP_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_WARP)) > 0)
@@ -495,15 +505,15 @@ int launch_symbolic_bins(mhb_context *h)
         constexpr int G = 32, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, 3 * GPB), cap_blocks), kSymThreads,
-               GPB * SB_BM_WARP_WORDS * 4, bins + off[SB_BM_WARP], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
-               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>(), (unsigned *)nullptr, (int *)nullptr, a_twins);
+               GPB * SB_BM_WARP_WORDS * 4, list(SB_BM_WARP), h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               SB_BM_WARP_WORDS, h->bsame.as<unsigned char>(), (unsigned *)nullptr, (int *)nullptr, a_twins, 0, scal);
     }
     if ((n = n_of(SB_H_G8)) > 0)
     {
         constexpr int G = 8, GPB = kSymThreads / G;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
-               GPB * 2 * SB_H_G8_SLOTS * 4, bins + off[SB_H_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               GPB * 2 * SB_H_G8_SLOTS * 4, list(SB_H_G8), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_G8_SLOTS), scal, probes);
     }
     if ((n = n_of(SB_BM_G8)) > 0)
@@ -519,14 +529,14 @@ int launch_symbolic_bins(mhb_context *h)
         }
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_sym_bitmap_group<G>, std::min(cdiv(n, 3 * GPB), cap_blocks), kSymThreads,
-               GPB * SB_BM_G8_WORDS * 4, bins + off[SB_BM_G8], n, h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               GPB * SB_BM_G8_WORDS * 4, list(SB_BM_G8), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                SB_BM_G8_WORDS, h->bsame.as<unsigned char>(), h->have_bm_store ? h->bm_store.as<unsigned>() : nullptr,
-               h->have_bm_store ? h->bm_slot.as<int>() : nullptr, a_twins);
+               h->have_bm_store ? h->bm_slot.as<int>() : nullptr, a_twins, n, scal);
     }
     if ((n = n_of(SB_TINY)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, bins + off[SB_TINY], n,
+        LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, list(SB_TINY),
                   h->Ap, h->Ac, tp, tc, tm, counts);
     }
     return join_bins(h);
@@ -625,6 +635,19 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
                       bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
+    }
+    if ((n = n_of(NB_H_BLOCK_XS)) > 0)
+    {
+        // 2 048-slot tables: 36 KB per row instead of the 4 096-slot bin's 74 KB, i.e. twice the rows in flight
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        if (h->claim_list)
+        {
+            if (int e_ = launch_hash_list(NB_H_BLOCK_XS, NB_H_BLOCK_XS_SLOTS, 128, cap_blocks * 2)) return e_;
+        }
+        else
+            LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
+                      bins + off[NB_H_BLOCK_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                       log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
@@ -791,7 +814,7 @@ float ev_ms(mhb_context *h, int a, int b)
 }
 
 int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, int nnzB,
-                const int *Bp, const int *Bc, int *Cp, long long *nnzC_out)
+                const int *Bp, const int *Bc, int *Cp, long long *nnzC_out, bool allow_spec = true)
 {
     if (M < 0 || K < 0 || N < 0 || nnzA < 0 || nnzB < 0)
         return fail(h, MHB_ERR_ARG, "negative dimension");
@@ -857,20 +880,36 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     rc = run_binning(h, M, SB_COUNT, h->bins_sym.as<int>(), SC_SYM_SIZE, SC_SYM_OFF);
     if (rc)
         return rc;
-    CU(cudaMemcpyAsync(hs, scal, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(h->ev[EV_SYMBIN], h->stream));
-    CU(cudaStreamSynchronize(h->stream)); // read #1: symbolic bin sizes
-    std::memcpy(h->sym_off, hs + SC_SYM_OFF, sizeof(h->sym_off));
-    h->max_tileflop = hs[SC_MAX_TILEFLOP];
-    std::memcpy(&h->stats.intprod, hs + SC_INTPROD_LO, 8);
-    std::memcpy(&h->stats.tileflop, hs + SC_TILEFLOP_LO, 8);
-    std::memcpy(&h->stats.ntiles_B, hs + SC_NTILES_LO, 8);
-    std::memcpy(h->stats.sym_bin_size, hs + SC_SYM_SIZE, sizeof(int) * MHB_MAX_BINS);
+    // Speculative launch: when the previous call on this handle had the same shape, its bin sizes
+    // size the grids and scratch of this call's symbolic kernels, the kernels read their row
+    // ranges from the device-side offsets, and host read #1 (a blocking round trip in the middle
+    // of the pipeline) is dropped; the guess is verified at the hand-off read below, and a miss
+    // (a bin that was not launched turned out populated, or a scratch capacity was exceeded)
+    // re-runs the phase the ordinary way.
+    const int key[5] = {M, K, N, nnzA, nnzB};
+    const bool spec = allow_spec && h->speculate && h->spec_ok && std::memcmp(key, h->spec_key, sizeof(key)) == 0;
+    h->spec_ok = false;
+    if (!spec)
+    {
+        CU(cudaMemcpyAsync(hs, scal, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev[EV_SYMBIN], h->stream));
+        CU(cudaStreamSynchronize(h->stream)); // read #1: symbolic bin sizes
+        std::memcpy(h->sym_off, hs + SC_SYM_OFF, sizeof(h->sym_off));
+        h->max_tileflop = hs[SC_MAX_TILEFLOP];
+    }
+    else
+    {
+        ++h->spec_calls;
+        CU(cudaEventRecord(h->ev[EV_SYMBIN], h->stream));
+    }
+    int launched[MHB_MAX_BINS + 1];
+    std::memcpy(launched, h->sym_off, sizeof(launched));
+    const int planned_tileflop = h->max_tileflop;
 
     // family 3: nnz per C row
     if (h->asame_early && !h->serial)
         CU(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
-    rc = launch_symbolic_bins(h);
+    rc = launch_symbolic_bins(h, spec);
     if (rc)
         return rc;
     CU(cudaEventRecord(h->ev[EV_SYM], h->stream));
@@ -892,6 +931,29 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     rc = check_dev_error(h, hs);
     if (rc)
         return rc;
+    if (spec)
+    {
+        bool miss = hs[SC_SPEC_MISS] != 0;
+        for (int b = 1; b < SB_COUNT; ++b) // bin 0 (rows without products) has no kernel
+            miss |= hs[SC_SYM_SIZE + b] > 0 && launched[b + 1] == launched[b];
+        // the global tile-hash pool was sized from the previous call's largest row (checked per row in the kernel too)
+        miss |= hs[SC_SYM_SIZE + SB_H_GLOBAL] > 0 && hs[SC_MAX_TILEFLOP] > planned_tileflop;
+        if (miss)
+        {
+            ++h->spec_misses;
+            return do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC_out, false);
+        }
+    }
+    std::memcpy(h->sym_off, hs + SC_SYM_OFF, sizeof(h->sym_off));
+    h->max_tileflop = hs[SC_MAX_TILEFLOP];
+    std::memcpy(&h->stats.intprod, hs + SC_INTPROD_LO, 8);
+    std::memcpy(&h->stats.tileflop, hs + SC_TILEFLOP_LO, 8);
+    std::memcpy(&h->stats.ntiles_B, hs + SC_NTILES_LO, 8);
+    std::memcpy(h->stats.sym_bin_size, hs + SC_SYM_SIZE, sizeof(int) * MHB_MAX_BINS);
+    h->stats.speculative_launches = h->spec_calls;
+    h->stats.speculative_misses = h->spec_misses;
+    std::memcpy(h->spec_key, key, sizeof(key));
+    h->spec_ok = true;
     std::memcpy(h->num_off, hs + SC_NUM_OFF, sizeof(h->num_off));
     h->max_rownnz = hs[SC_MAX_ROWNNZ];
     std::memcpy(&h->nnzC, hs + SC_NNZC_LO, 8);
@@ -1286,6 +1348,8 @@ extern "C"
             h->count_probes = (int)value;
         else if (k == "mask_onepass")
             h->mask_onepass = (int)value;
+        else if (k == "speculate")
+            h->speculate = (int)value;
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")

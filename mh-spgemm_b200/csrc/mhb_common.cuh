@@ -106,6 +106,20 @@ struct Unset<float>
     static __device__ __forceinline__ bool is(float v) { return __float_as_int(v) == 0x7F800001; }
 };
 
+// The rows of one bin, as a kernel argument.  Normally the host knows the bin's range
+// (n >= 0, rows points at the bin's first entry).  In a SPECULATIVE symbolic launch (the
+// host has not read the bin sizes of this call yet and sizes its grids from the previous call
+// on the handle) n is -1 and the range is read from the device-side offsets: rows = the start of
+// the whole bin list, off = &offsets[bin].
+struct RowList
+{
+    const int *rows;
+    const int *off;
+    int n;
+    __device__ __forceinline__ const int *begin() const { return n >= 0 ? rows : rows + off[0]; }
+    __device__ __forceinline__ int size() const { return n >= 0 ? n : off[1] - off[0]; }
+};
+
 // error flags raised by kernels (checked by the host at the next synchronisation point)
 enum DevError
 {
@@ -123,12 +137,13 @@ enum Scalar
     SC_MAX_TILEFLOP = 8,
     SC_MAX_ROWNNZ = 9,
     SC_ERROR = 10,
+    SC_SPEC_MISS = 11,     // a speculative symbolic launch met a capacity it had not planned for: redo
     SC_PROBES_LO = 12,     // unsigned long long at [12..13]: failed probes of the numeric hash kernels (option count_probes)
     SC_SYM_PROBES_LO = 14, // unsigned long long at [14..15]: same for the symbolic tile hash
     SC_SYM_SIZE = 16,               // MHB_MAX_BINS ints
-    SC_SYM_OFF = 32,                // MHB_MAX_BINS + 1 ints
-    SC_NUM_SIZE = 64,               // MHB_MAX_BINS ints
-    SC_NUM_OFF = 80,                // MHB_MAX_BINS + 1 ints
+    SC_SYM_OFF = 40,                // MHB_MAX_BINS + 1 ints
+    SC_NUM_SIZE = 72,               // MHB_MAX_BINS ints
+    SC_NUM_OFF = 96,                // MHB_MAX_BINS + 1 ints
     SC_COUNT = 128
 };
 

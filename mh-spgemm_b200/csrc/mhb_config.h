@@ -12,7 +12,7 @@
 #define MHB_TILE_SHIFT 5 // 32-column tiles, as inc/common.h:74-75
 #define MHB_TILE_BITS 32
 
-#define MHB_MAX_BINS 16
+#define MHB_MAX_BINS 24
 #define MHB_SMEM_MAX 232448 // 227 KB opt-in dynamic shared memory per block on sm_100
 
 // ---- symbolic bins (family 3). Wt = 32-column words spanned by the C row, tf = tile-flop,
@@ -65,6 +65,7 @@ enum MhbNumBin
     NB_WIN_COMPACT, // window rows with a stored symbolic bitmap, n <= 448: rank-mapped accumulators,
                     // up to three twin rows of A per warp
     NB_H_BLOCK_M,   // hash, block/row,   n <= 5120 (8192 slots, claim list)
+    NB_H_BLOCK_XS,  // hash, block/row,   n <= 1280 (2048 slots, claim list, 128 threads)
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -81,6 +82,8 @@ enum MhbNumBin
 #define NB_H_WARP_S_MAX 160
 #define NB_H_WARP_L_SLOTS 1024
 #define NB_H_WARP_L_MAX 640
+#define NB_H_BLOCK_XS_SLOTS 2048
+#define NB_H_BLOCK_XS_MAX 1280
 #define NB_H_BLOCK_S_SLOTS 4096
 #define NB_H_BLOCK_S_MAX 2560
 #define NB_H_BLOCK_M_SLOTS 8192
@@ -169,6 +172,8 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf
         return NB_H_WARP_M;
     if (n <= NB_H_WARP_L_MAX)
         return NB_H_WARP_L;
+    if (n <= NB_H_BLOCK_XS_MAX)
+        return NB_H_BLOCK_XS;
     if (n <= NB_H_BLOCK_S_MAX)
         return NB_H_BLOCK_S;
     if (n <= NB_H_BLOCK_M_MAX)

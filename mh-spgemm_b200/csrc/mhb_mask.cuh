@@ -238,7 +238,7 @@ __device__ __forceinline__ long long chained_scan_lookback(unsigned long long *s
 
 // ctrl[0] = chunk ticket counter (zeroed with the scalars); status[nchunks] zeroed likewise;
 // flags[] holds the row-start bits on entry and the complete tile-start flags on exit.
-__global__ void __launch_bounds__(kMaskThreads)
+__global__ void __launch_bounds__(kMaskThreads, 5)
     k_mask_build(const int *__restrict__ Bc, long long nnz, long long nwords, unsigned *flags,
                  int *__restrict__ wordprefix, int *__restrict__ tilecol, unsigned *__restrict__ tilemask,
                  unsigned *__restrict__ ctrl, unsigned long long *__restrict__ status, int nchunks,
@@ -254,25 +254,24 @@ __global__ void __launch_bounds__(kMaskThreads)
     __syncthreads();
     const int chunk = sh_chunk;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const long long w0 = (long long)chunk * kMaskChunkWords + (long long)warp * WPW; // first word of this warp
+    // positions are 32-bit: nnz(B) < 2^31 by the int32 CSR contract, and a chunk overruns it by < 2^12
+    const unsigned w0 = (unsigned)chunk * kMaskChunkWords + (unsigned)warp * WPW; // first word of this warp
+    const unsigned n32 = (unsigned)nnz;
     // columns of the warp's WPW words plus one look-ahead word, all loads issued up front
     int c[WPW + 1];
 #pragma unroll
     for (int i = 0; i <= WPW; ++i)
     {
-        const long long j = (w0 + i) * 32 + lane;
-        c[i] = (j < nnz) ? __ldg(&Bc[j]) : -1;
+        const unsigned j = (w0 + i) * 32 + lane;
+        c[i] = (j < n32) ? __ldg(&Bc[j]) : -1;
     }
     int prev_last = -1; // column in front of the warp's first nonzero
-    {
-        const long long j = w0 * 32 - 1;
-        if (j >= 0 && j < nnz)
-            prev_last = __ldg(&Bc[j]);
-    }
+    if (w0 > 0 && w0 * 32 - 1 < n32)
+        prev_last = __ldg(&Bc[w0 * 32 - 1]);
     unsigned rowbits[WPW + 1];
 #pragma unroll
     for (int i = 0; i <= WPW; ++i)
-        rowbits[i] = (w0 + i < nwords) ? flags[w0 + i] : 0u; // row starts (or already-complete flags: a superset)
+        rowbits[i] = (w0 + i < (unsigned)nwords) ? flags[w0 + i] : 0u; // row starts (or already-complete flags: a superset)
     // tile-start flags: the tile column changes, or a row starts
     unsigned f[WPW + 1];
     int tiles = 0;
@@ -308,8 +307,8 @@ __global__ void __launch_bounds__(kMaskThreads)
 #pragma unroll
     for (int i = 0; i < WPW; ++i)
     {
-        const long long word = w0 + i;
-        if (word >= nwords)
+        const unsigned word = w0 + i;
+        if (word >= (unsigned)nwords)
             break;
         const unsigned fi = f[i];
         if (lane == 0)
@@ -317,27 +316,23 @@ __global__ void __launch_bounds__(kMaskThreads)
             flags[word] = fi;
             wordprefix[word] = (int)run;
         }
-        // mask of every run that STARTS in this word: segmented suffix-OR inside the word ...
+        // mask of every run that STARTS in this word: OR over the lanes of the run (lanes with the
+        // same number of tile starts at or before them), by match + redux instead of a
+        // five-step segmented shuffle scan ...
         const bool valid = c[i] >= 0;
-        unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
-        const unsigned above = (lane == 31) ? 0u : (fi >> (lane + 1));
-        const int seg_end = above ? lane + __ffs(above) - 1 : 31; // last lane of this lane's run inside the word
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const unsigned v = __shfl_down_sync(kFull, bits, d);
-            if (lane + d <= seg_end)
-                bits |= v;
-        }
+        const unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
+        const int rid = __popc(fi & lanemask_le());
+        const unsigned peers = __match_any_sync(kFull, rid);
+        const unsigned inword = __reduce_or_sync(peers, bits);
         // ... plus the run's continuation in the leading lanes of the next word
         const unsigned fn = f[i + 1];
         const int lead = fn ? __ffs(fn) - 1 : 32;
         const unsigned ext = __reduce_or_sync(kFull, (lane < lead && c[i + 1] >= 0) ? (1u << (c[i + 1] & 31)) : 0u);
         if (valid && ((fi >> lane) & 1u))
         {
-            const int t = (int)run + __popc(fi & lanemask_lt());
+            const int t = (int)run + rid - 1;
             tilecol[t] = c[i] >> MHB_TILE_SHIFT;
-            tilemask[t] = (seg_end == 31) ? (bits | ext) : bits;
+            tilemask[t] = (rid == __popc(fi)) ? (inword | ext) : inword; // the word's last run may continue
         }
         run += __popc(fi);
     }

@@ -39,14 +39,24 @@ constexpr int kSymThreads = 256;
 // three rows need no work.
 template <int G>
 __global__ void __launch_bounds__(kSymThreads)
-    k_sym_bitmap_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_sym_bitmap_group(RowList list, const int *__restrict__ Ap,
                        const int *__restrict__ Ac, const int *__restrict__ tileptr,
                        const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                        const int4 *__restrict__ arow, int *__restrict__ counts, int wcap,
                        const unsigned char *__restrict__ same, unsigned *__restrict__ bm_store,
-                       int *__restrict__ bm_slot, const unsigned char *__restrict__ asame)
+                       int *__restrict__ bm_slot, const unsigned char *__restrict__ asame, int bm_cap,
+                       int *__restrict__ scal)
 {
     extern __shared__ unsigned sm_u[];
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
+    if (bm_store && nrows > bm_cap) // speculative launch sized the bitmap store for fewer rows: redo
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicMax(scal + SC_SPEC_MISS, 1);
+        bm_store = nullptr;
+        bm_slot = nullptr;
+    }
     constexpr int NG = 32 / G, WIN = 3 * NG, WPB = kSymThreads / 32;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
@@ -182,13 +192,15 @@ __device__ __forceinline__ int block_sum_int(int v, int *sh /*32*/)
 
 // ---- bitmap, one block per row (Wt up to 57 344 words) ---------------------------------
 __global__ void __launch_bounds__(kSymThreads)
-    k_sym_bitmap_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_sym_bitmap_block(RowList list, const int *__restrict__ Ap,
                        const int *__restrict__ Ac, const int *__restrict__ tileptr,
                        const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                        const int4 *__restrict__ arow, int *__restrict__ counts)
 {
     extern __shared__ unsigned sm_u[];
     __shared__ int red[32];
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     unsigned *bm = sm_u;
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x)
@@ -283,7 +295,7 @@ __device__ __forceinline__ int tile_insert_lockstep(unsigned gm, int *keys, unsi
 
 template <int G>
 __global__ void __launch_bounds__(kSymThreads)
-    k_sym_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_sym_hash_group(RowList list, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const int *__restrict__ tileptr,
                      const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                      const int4 *__restrict__ arow, int *__restrict__ counts, int logS, int *__restrict__ scal,
@@ -291,6 +303,8 @@ __global__ void __launch_bounds__(kSymThreads)
 {
     extern __shared__ unsigned sm_u[];
     constexpr int GPB = kSymThreads / G;
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     int np = 0;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
@@ -300,13 +314,15 @@ __global__ void __launch_bounds__(kSymThreads)
     for (int r = blockIdx.x * GPB + g; r < nrows; r += gridDim.x * GPB)
     {
         const int row = rows[r];
-        // table of THIS row: power of two >= 4/3 of its tile upper bound min(tile-flop, spanned
-        // words); initialisation and the popcount sweep then scale with the row, not the bin
+        // table of THIS row: power of two >= 2x its tile upper bound min(tile-flop, spanned words),
+        // at most the bin's; initialisation and the popcount sweep then scale with the row, not
+        // the bin (a 4/3 bound was tried first: the lockstep probe loop runs as long as the
+        // unluckiest lane, and at fill 3/4 that cost more than the sweeps saved -- r2g)
         const int4 info = __ldg(&arow[row]);
         const int wt = (info.w >> MHB_TILE_SHIFT) - (info.z >> MHB_TILE_SHIFT) + 1;
         const int ub = min(info.y, wt);
         int lS = 5;
-        while (lS < logS && (1 << lS) * 3 < ub * 4)
+        while (lS < logS && (1 << lS) < ub * 2)
             ++lS;
         const int S = 1 << lS;
         for (int w = l; w < S; w += G)
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(kSymThreads)
 // One block per row; table in shared memory (pool == nullptr) or in a per-block slice of
 // the global pool (2 * pool_slots ints per block), sized per row from its tile upper bound.
 __global__ void __launch_bounds__(kSymThreads)
-    k_sym_hash_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_sym_hash_block(RowList list, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const int *__restrict__ tileptr,
                      const int *__restrict__ tilecol, const unsigned *__restrict__ tilemask,
                      const int4 *__restrict__ arow, int *__restrict__ counts, int logS_fixed,
@@ -344,6 +360,8 @@ __global__ void __launch_bounds__(kSymThreads)
 {
     extern __shared__ unsigned sm_u[];
     __shared__ int red[32];
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     int np = 0;
     const int warp = threadIdx.x >> 5, lane = lane_id(), nwarp = blockDim.x >> 5;
     for (int r = blockIdx.x; r < nrows; r += gridDim.x)
@@ -360,6 +378,12 @@ __global__ void __launch_bounds__(kSymThreads)
             logS = 10;
             while ((1LL << logS) < ub + (ub >> 1) + 1)
                 ++logS;
+            if ((1LL << logS) > pool_slots) // the speculative launch sized the pool for smaller rows: redo
+            {
+                if (threadIdx.x == 0)
+                    atomicMax(scal + SC_SPEC_MISS, 1);
+                continue;
+            }
             keys = pool + (size_t)blockIdx.x * 2 * pool_slots;
         }
         else
@@ -367,8 +391,8 @@ __global__ void __launch_bounds__(kSymThreads)
             const int4 info = arow[row];
             const int wt = (info.w >> MHB_TILE_SHIFT) - (info.z >> MHB_TILE_SHIFT) + 1;
             const int ub = min(info.y, wt);
-            logS = 8; // the row's own table: power of two >= 4/3 ub, at most the bin's
-            while (logS < logS_fixed && (1 << logS) * 3 < ub * 4)
+            logS = 8; // the row's own table: power of two >= 2 ub, at most the bin's
+            while (logS < logS_fixed && (1 << logS) < ub * 2)
                 ++logS;
             keys = (int *)sm_u;
         }
@@ -406,10 +430,12 @@ __global__ void __launch_bounds__(kSymThreads)
 constexpr int kTinyThreads = 256;
 
 __global__ void __launch_bounds__(kTinyThreads)
-    k_sym_tiny(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap, const int *__restrict__ Ac,
+    k_sym_tiny(RowList list, const int *__restrict__ Ap, const int *__restrict__ Ac,
                const int *__restrict__ tileptr, const int *__restrict__ tilecol,
                const unsigned *__restrict__ tilemask, int *__restrict__ counts)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     __shared__ int keys[SB_TINY_MAX * kTinyThreads];
     __shared__ unsigned masks[SB_TINY_MAX * kTinyThreads];
     const int t = threadIdx.x;

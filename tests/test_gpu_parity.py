@@ -600,3 +600,40 @@ def test_row_sharded_spgemm_multi_rank(world):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     # the ranks print concurrently: count the tokens, not the lines
     assert p.returncode == 0 and p.stdout.count("SHARD-OK") == 5 * world, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def test_speculative_symbolic_launch_and_miss(orc):
+    """A call with the shape of the previous one launches its symbolic kernels from that call's
+    bin sizes (no mid-pipeline host read).  Same pattern again: speculative, no miss.  Same
+    SHAPE (M, K, N, nnz) but a pattern that lands in bins the previous call never populated:
+    the guess must be detected as a miss and the result must still be exact."""
+    t = api.Tool(0)
+    A1 = G.poisson2d(64)  # every row in the tiny bins
+    assert (A1.M, A1.nnz) == (4096, 20224)
+    Cp, Cc, Cv = orc.spgemm(A1, A1)
+    assert_matches(orc, t.spgemm_host(A1, A1), Cp, Cc, Cv)
+    assert t.stats["speculative_launches"] == 0
+    assert_matches(orc, t.spgemm_host(A1, A1), Cp, Cc, Cv)
+    st = t.stats
+    assert st["speculative_launches"] == 1 and st["speculative_misses"] == 0
+    # 100 rows of 200 nonzeros that all select each other (20 000 products per C row) + 224 singletons
+    rng = np.random.default_rng(7)
+    rows, cols = [], []
+    for r in range(100):
+        c = np.concatenate([np.arange(100), 100 + np.sort(rng.choice(3996, 100, replace=False))])
+        rows.append(np.full(200, r)), cols.append(c)
+    rows.append(np.arange(100, 324)), cols.append(rng.integers(0, 4096, 224))
+    A2 = CSR.from_coo(4096, 4096, np.concatenate(rows), np.concatenate(cols), rng=rng)
+    assert (A2.M, A2.nnz) == (A1.M, A1.nnz)
+    C2 = t.spgemm_host(A2, A2)
+    Cp2, Cc2, Cv2 = orc.spgemm(A2, A2)
+    assert_matches(orc, C2, Cp2, Cc2, Cv2)
+    st = t.stats
+    assert st["speculative_launches"] == 2 and st["speculative_misses"] == 1
+    # and back: the big-row bins of A2 are launched for A1 and find nothing to do
+    assert_matches(orc, t.spgemm_host(A1, A1), Cp, Cc, Cv)
+    assert t.stats["speculative_misses"] == 1
+    t.set_option("speculate", 0)
+    assert_matches(orc, t.spgemm_host(A2, A2), Cp2, Cc2, Cv2)
+    assert t.stats["speculative_launches"] == 3
+    t.release()
