@@ -316,23 +316,30 @@ __global__ void __launch_bounds__(kMaskThreads, 5)
             flags[word] = fi;
             wordprefix[word] = (int)run;
         }
-        // mask of every run that STARTS in this word: OR over the lanes of the run (lanes with the
-        // same number of tile starts at or before them), by match + redux instead of a
-        // five-step segmented shuffle scan ...
+        // mask of every run that STARTS in this word: segmented suffix-OR inside the word.  (A
+        // match_any + redux.or formulation was measured and lost -- 44 -> 54 us on the cant-like
+        // input, 36 -> 121 us on the R-MAT where every lane is its own run: MATCH.ANY takes one
+        // round per distinct value.  profiles/r2_launches_F.md)
         const bool valid = c[i] >= 0;
-        const unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
-        const int rid = __popc(fi & lanemask_le());
-        const unsigned peers = __match_any_sync(kFull, rid);
-        const unsigned inword = __reduce_or_sync(peers, bits);
+        unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
+        const unsigned above = (lane == 31) ? 0u : (fi >> (lane + 1));
+        const int seg_end = above ? lane + __ffs(above) - 1 : 31; // last lane of this lane's run inside the word
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned v = __shfl_down_sync(kFull, bits, d);
+            if (lane + d <= seg_end)
+                bits |= v;
+        }
         // ... plus the run's continuation in the leading lanes of the next word
         const unsigned fn = f[i + 1];
         const int lead = fn ? __ffs(fn) - 1 : 32;
         const unsigned ext = __reduce_or_sync(kFull, (lane < lead && c[i + 1] >= 0) ? (1u << (c[i + 1] & 31)) : 0u);
         if (valid && ((fi >> lane) & 1u))
         {
-            const int t = (int)run + rid - 1;
+            const int t = (int)run + __popc(fi & lanemask_lt());
             tilecol[t] = c[i] >> MHB_TILE_SHIFT;
-            tilemask[t] = (rid == __popc(fi)) ? (inword | ext) : inword; // the word's last run may continue
+            tilemask[t] = (seg_end == 31) ? (bits | ext) : bits;
         }
         run += __popc(fi);
     }
