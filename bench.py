@@ -374,7 +374,8 @@ def main():
     import torch.distributed as dist
     from mh_spgemm_b200 import api
     from mh_spgemm_b200.distributed import (RangeExchange, Shard, ShardedSpGEMM, SliceSizes, b_views, column_range,
-                                            pack_b, partition_rows, row_work, slice_rows_fast)
+                                            pack_b, partition_rows, row_cost, row_work, slice_rows_fast,
+                                            snap_to_pattern_change)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -405,7 +406,9 @@ def main():
     B = A
     work = row_work(A, B)
     intprod = int(work.sum())
-    bounds = partition_rows(work, world)
+    # row blocks balanced by a per-row cost (products, inflated for long rows), never cutting a
+    # run of twin rows
+    bounds = snap_to_pattern_change(A, partition_rows(row_cost(work), world))
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     Ablk = A.rows(r0, r1)
     tool = api.Tool(local)
@@ -423,14 +426,26 @@ def main():
     exch_bytes = 0
     k0, k1 = 0, B.M
 
+    c_buf = {}  # the caller's C arrays, kept across steps and regrown only when a slice needs more room
+
     def multiply(sym, num):
-        """symbolic + allocation + numeric per slice; returns the last slice and the rank's nnz."""
+        """symbolic + allocation of C + numeric per slice; returns the last slice and the rank's nnz.
+        C.ptr / C.col / C.val are caller-owned (the hand-off of src/main.cu:55-60): a caller that
+        multiplies repeatedly keeps its buffers, so they are allocated on the first step (and
+        whenever nnz outgrows them) and reused afterwards; with one slice per rank nothing is
+        shared between slices."""
         total, last = 0, None
-        for s0, s1 in slices:
-            cp = torch.empty(s1 - s0 + 1, dtype=torch.int32, device=dev)
+        for i, (s0, s1) in enumerate(slices):
+            key = i if len(slices) == 1 else 0  # many slices (C beyond int32): one set of buffers, reused in turn
+            if key not in c_buf or c_buf[key][0].numel() < s1 - s0 + 1:
+                c_buf[key] = [torch.empty(s1 - s0 + 1, dtype=torch.int32, device=dev), None, None]
+            cp = c_buf[key][0][:s1 - s0 + 1]
             nnz = sym(s0, s1, cp)
-            ccol = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-            cval = torch.empty(max(nnz, 1), dtype=dt, device=dev)
+            if c_buf[key][1] is None or c_buf[key][1].numel() < nnz:
+                c_buf[key][1] = c_buf[key][2] = None
+                c_buf[key][1] = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+                c_buf[key][2] = torch.empty(max(nnz, 1), dtype=dt, device=dev)
+            ccol, cval = c_buf[key][1], c_buf[key][2]
             num(ccol, cval)
             total += nnz
             last = (s0, s1, cp, ccol[:nnz], cval[:nnz])
@@ -665,7 +680,7 @@ def main():
         kernels = sorted({NUM_KERNEL.get(k, k) for k in nb})
         traffic, capture = captured_traffic(args.workload, world)
         par = {"single": "single GPU",
-               "peer": f"A row-sharded x{world} by product count; B row-sharded like A, every rank pulls the B rows its "
+               "peer": f"A row-sharded x{world} by per-row cost (products, long rows weighted up); B row-sharded like A, every rank pulls the B rows its "
                        "block references out of the owners' CUDA-IPC windows (one-sided, NVLink), C ABI mhb_shard_*",
                "broadcast": f"A row-sharded x{world} by product count; B ncclBroadcast from rank 0 each step (C++), "
                             "slice sizes by NCCL all-gather",

