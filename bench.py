@@ -79,7 +79,7 @@ def bytes_alg(A: CSR, B: CSR, nnzC: int, w: int = 8) -> int:
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML every ~2 ms while the timed region
+    """SM clock and throttle reasons sampled through NVML every ~5 ms while the timed region
     runs (the nvidia-smi line of B200_PROFILING.md, in-process so that a region of a few
     milliseconds still gets samples)."""
 
@@ -115,7 +115,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def mark(self):
         """Forget what was sampled so far (warm-up); keep sampling."""
@@ -556,6 +556,9 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     num_ms, launches = [], 0
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pause inside a 0.5 ms step
     for k in range(args.steps):
         # evict L2 between timed iterations (outside the event pair): write 256 MiB, then read it
         # back so that L2 is left full of CLEAN lines -- after a write-only flush the step also
@@ -570,6 +573,7 @@ def main():
         num_ms.append(tool.timing.Numeric)
         launches += tool.stats["gpu_launches"] * len(slices) + (3 if mode == "peer" else 0)
     torch.cuda.synchronize()
+    gc.enable()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
