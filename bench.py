@@ -352,6 +352,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suite", action="store_true", help="skip the 12-matrix breadth check (N=1, workload F only)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--contract", default="fused", choices=["fused", "two-phase"],
+                    help="'fused' = mhb_spgemm_into_* (C arrays kept by the caller, one host synchronisation per "
+                         "SpGEMM); 'two-phase' = mhb_symbolic, then mhb_numeric_* (the reference's hand-off as two calls)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "broadcast", "sendrecv"],
                     help="N>1: 'peer' = B row-sharded like A, every rank pulls the B rows its block references out of "
                          "the owners' CUDA-IPC windows (mhb_shard_*, one-sided over NVLink); 'broadcast' = B on "
@@ -428,34 +431,57 @@ def main():
 
     c_buf = {}  # the caller's C arrays, kept across steps and regrown only when a slice needs more room
 
-    def multiply(sym, num):
-        """symbolic + allocation of C + numeric per slice; returns the last slice and the rank's nnz.
+    def multiply(into):
+        """One SpGEMM per slice into the caller's C arrays; returns the last slice and the rank's nnz.
         C.ptr / C.col / C.val are caller-owned (the hand-off of src/main.cu:55-60): a caller that
         multiplies repeatedly keeps its buffers, so they are allocated on the first step (and
-        whenever nnz outgrows them) and reused afterwards; with one slice per rank nothing is
-        shared between slices."""
+        whenever nnz outgrows them: the call reports MHB_ERR_CAPACITY with the size it needs) and
+        reused afterwards; with one slice per rank nothing is shared between slices."""
         total, last = 0, None
         for i, (s0, s1) in enumerate(slices):
             key = i if len(slices) == 1 else 0  # many slices (C beyond int32): one set of buffers, reused in turn
             if key not in c_buf or c_buf[key][0].numel() < s1 - s0 + 1:
                 c_buf[key] = [torch.empty(s1 - s0 + 1, dtype=torch.int32, device=dev), None, None]
-            cp = c_buf[key][0][:s1 - s0 + 1]
-            nnz = sym(s0, s1, cp)
-            if c_buf[key][1] is None or c_buf[key][1].numel() < nnz:
-                c_buf[key][1] = c_buf[key][2] = None
-                c_buf[key][1] = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
-                c_buf[key][2] = torch.empty(max(nnz, 1), dtype=dt, device=dev)
-            ccol, cval = c_buf[key][1], c_buf[key][2]
-            num(ccol, cval)
+            buf = c_buf[key]
+            cp = buf[0][:s1 - s0 + 1]
+            try:
+                nnz = into(s0, s1, cp, buf[1], buf[2])
+            except api.MhbError as e:
+                if e.code != api.ERR_CAPACITY:
+                    raise
+                buf[1] = buf[2] = None
+                buf[1] = torch.empty(max(e.nnzC, 1), dtype=torch.int32, device=dev)
+                buf[2] = torch.empty(max(e.nnzC, 1), dtype=dt, device=dev)
+                nnz = into(s0, s1, cp, buf[1], buf[2])
             total += nnz
-            last = (s0, s1, cp, ccol[:nnz], cval[:nnz])
+            last = (s0, s1, cp, buf[1][:nnz], buf[2][:nnz])
         return last, total
 
+    def two_phase(sym, num):
+        """The reference's contract as two calls (symbolic -> caller sizes C -> numeric), behind the
+        same signature as the fused call: --contract two-phase."""
+        def into(s0, s1, cp, cc, cv):
+            nnz = sym(s0, s1, cp)
+            if cc is None or cc.numel() < nnz:
+                e = api.MhbError(api.ERR_CAPACITY, "grow C")
+                e.nnzC = nnz
+                raise e
+            num(cc, cv)
+            return nnz
+        return into
+
+    fused = args.contract == "fused"
     if mode == "single":
+        if fused:
+            into = lambda s0, s1, cp, cc, cv: tool.spgemm_into(s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_val, a_ptr, a_col,
+                                                               a_val, cp, cc, cv)
+        else:
+            into = two_phase(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_ptr,
+                                                                   a_col, cp),
+                             lambda cc, cv: tool.numeric_into(a_val, a_val, cc, cv))
+
         def one_step():  # B = A: one copy on the device, aliasing visible to the library
-            return multiply(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_ptr,
-                                                                  a_col, cp),
-                            lambda cc, cv: tool.numeric_into(a_val, a_val, cc, cv))
+            return multiply(into)
     elif mode == "peer":
         Bown = B.rows(r0, r1)  # B = A is sharded like A
         dBp = torch.from_numpy(Bown.ptr).to(dev)
@@ -466,6 +492,10 @@ def main():
         k0, k1, _, exch_bytes = sh.image()
 
         trace = []  # MHB_BENCH_TRACE=1: device time of exchange / multiply / size post per step
+        if fused:
+            into = lambda s0, s1, cp, cc, cv: sh.spgemm_into(s0, s1, a_val, cp, cc, cv)
+        else:
+            into = two_phase(lambda s0, s1, cp: sh.symbolic(s0, s1, cp), lambda cc, cv: sh.numeric_into(a_val, cc, cv))
 
         def one_step():
             tr = os.environ.get("MHB_BENCH_TRACE") == "1"
@@ -475,8 +505,7 @@ def main():
             sh.exchange()
             if tr:
                 e[1].record(stream)
-            last, total = multiply(lambda s0, s1, cp: sh.symbolic(s0, s1, cp),
-                                   lambda cc, cv: sh.numeric_into(a_val, cc, cv))
+            last, total = multiply(into)
             if tr:
                 e[2].record(stream)
             sh.post_size(total)
@@ -492,12 +521,16 @@ def main():
         Bbuf = packed.to(dev) if rank == 0 else torch.empty_like(packed, device=dev)
         exch_bytes = 0 if rank == 0 else packed.numel()
         bp, bc, bv = b_views(Bbuf, B.M, B.nnz, dt)
+        if fused:
+            into = lambda s0, s1, cp, cc, cv: tool.spgemm_into(s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_val, bp, bc, bv,
+                                                               cp, cc, cv)
+        else:
+            into = two_phase(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, bp, bc, cp),
+                             lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
 
         def one_step():
             sh.broadcast(Bbuf, Bbuf.numel(), 0)  # ncclBroadcast issued from C++ on the Tool's stream
-            last, total = multiply(
-                lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, bp, bc, cp),
-                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
+            last, total = multiply(into)
             sizes.gather(total)
             return last, total
     else:  # sendrecv: the round-1 exchange (torch.distributed grouped send/recv), kept as the fallback
@@ -516,10 +549,10 @@ def main():
 
         def one_step():
             bp, bc, bv = plan.run(own_col, own_val)
-            last, total = multiply(
+            last, total = multiply(two_phase(
                 lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, plan.K_local, B.N, a_ptr[s0:], a_shift, bp,
                                                       bc[:plan.nnz_local], cp),
-                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
+                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv)))
             sizes.gather(total)
             return last, total
 
@@ -694,7 +727,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(cfg, intprod=intprod, nnzC=nnzC_total),
-            "l2": L2_NOTE, "parallelism": par, "exchange_bytes_received_rank0": exch_bytes, "slices_rank0": len(slices),
+            "l2": L2_NOTE, "parallelism": par,
+            "call": ("mhb_spgemm_into_f64: caller-owned C arrays kept across steps, one host synchronisation per SpGEMM"
+                     if fused else "mhb_symbolic + mhb_numeric_f64: two calls, host reads nnz(C) in between"),
+            "fused_calls": stats.get("fused_calls"), "speculative_misses": stats.get("speculative_misses"), "exchange_bytes_received_rank0": exch_bytes, "slices_rank0": len(slices),
             "roofline": {"bound": "hbm",
                          "kernel": "numeric: " + " + ".join(kernels) + ("" if len(kernels) == 1 else " (bins run concurrently)"),
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

@@ -29,7 +29,8 @@ enum {
     MHB_ERR_CUDA = 1,      /* a CUDA runtime call or kernel failed */
     MHB_ERR_ARG = 2,       /* invalid argument / call order */
     MHB_ERR_OVERFLOW = 3,  /* nnz(C) does not fit the int32 CSR contract: shard the rows */
-    MHB_ERR_NOMEM = 4      /* device or pinned allocation failed */
+    MHB_ERR_NOMEM = 4,     /* device or pinned allocation failed */
+    MHB_ERR_CAPACITY = 5   /* mhb_spgemm_into_*: nnz(C) exceeds the caller's C.col / C.val capacity */
 };
 
 /* Per-stage device times of the last call, in ms, named after the reference's Timing
@@ -64,6 +65,8 @@ typedef struct mhb_stats {
      * re-run the ordinary way because the guess did not cover the input */
     int speculative_launches;
     int speculative_misses;
+    /* mhb_spgemm_into_* calls on this handle that ran with a single host synchronisation */
+    int fused_calls;
 } mhb_stats;
 
 /* ---- lifetime (replaces Tool::allocate / Tool::release, src/Tool.cu:4-69) ---- */
@@ -112,6 +115,23 @@ int mhb_spgemm_f32(mhb_handle_t h, int M, int K, int N,
                    int nnzA, const int *dA_ptr, const int *dA_col, const float *dA_val,
                    int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
                    int **dC_ptr, int **dC_col, float **dC_val, long long *nnzC);
+/* MH_spgemm into CALLER-OWNED C arrays: dC_ptr[M+1], dC_col / dC_val with room for `capacity`
+ * entries.  For the caller that multiplies repeatedly (the timed loop of src/main.cu:118-125
+ * re-allocates C every iteration, src/main.cu:59-60; a caller that keeps its buffers has nothing
+ * to allocate at the hand-off of src/main.cu:55-60).  When the call has the shape of the previous
+ * one on the handle, both phases are launched without any host read in between (bin sizes and
+ * nnz(C) stay on the device, the guess is verified by a device-side gate and re-run the ordinary
+ * way on a miss): ONE host synchronisation per SpGEMM, at the end.  If nnz(C) > capacity nothing
+ * is written to dC_col / dC_val, dC_ptr and *nnzC are valid and the call returns
+ * MHB_ERR_CAPACITY: grow the arrays and call again.  mhb_numeric_* may follow (pattern reuse). */
+int mhb_spgemm_into_f64(mhb_handle_t h, int M, int K, int N,
+                        int nnzA, const int *dA_ptr, const int *dA_col, const double *dA_val,
+                        int nnzB, const int *dB_ptr, const int *dB_col, const double *dB_val,
+                        int *dC_ptr, int *dC_col, double *dC_val, long long capacity, long long *nnzC);
+int mhb_spgemm_into_f32(mhb_handle_t h, int M, int K, int N,
+                        int nnzA, const int *dA_ptr, const int *dA_col, const float *dA_val,
+                        int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
+                        int *dC_ptr, int *dC_col, float *dC_val, long long capacity, long long *nnzC);
 int mhb_device_free(void *dptr);
 /* Raw device buffers and copies for callers without their own CUDA runtime binding: the
  * pieces of CSR::H2D / CSR::D2H (src/CSR.cu:97-120).  Synchronous. */
@@ -236,6 +256,12 @@ int mhb_shard_barrier(mhb_shard_t s);
 int mhb_shard_symbolic(mhb_shard_t s, int r_lo, int r_hi, int *dC_ptr, long long *nnzC);
 int mhb_shard_numeric_f64(mhb_shard_t s, const double *dA_val, int *dC_col, double *dC_val);
 int mhb_shard_numeric_f32(mhb_shard_t s, const float *dA_val, int *dC_col, float *dC_val);
+/* mhb_spgemm_into_* for rows [r_lo, r_hi) of this rank's block against the image: one host
+ * synchronisation per step (see mhb_spgemm_into_f64). */
+int mhb_shard_spgemm_into_f64(mhb_shard_t s, int r_lo, int r_hi, const double *dA_val, int *dC_ptr, int *dC_col,
+                              double *dC_val, long long capacity, long long *nnzC);
+int mhb_shard_spgemm_into_f32(mhb_shard_t s, int r_lo, int r_hi, const float *dA_val, int *dC_ptr, int *dC_col,
+                              float *dC_val, long long capacity, long long *nnzC);
 /* Publish this rank's nnz(C slice) of the step to every rank (one-sided, stream-ordered);
  * mhb_shard_offsets waits for all of them: offset of this rank's slice and the total. */
 int mhb_shard_post_size(mhb_shard_t s, long long nnzC_local);

@@ -32,6 +32,7 @@ NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8",
 ABI_SYMBOLS = [
     "mhb_version", "mhb_create", "mhb_destroy", "mhb_last_error", "mhb_set_stream", "mhb_set_option",
     "mhb_symbolic", "mhb_numeric_f64", "mhb_numeric_f32", "mhb_spgemm_f64", "mhb_spgemm_f32",
+    "mhb_spgemm_into_f64", "mhb_spgemm_into_f32", "mhb_shard_spgemm_into_f64", "mhb_shard_spgemm_into_f32",
     "mhb_device_free", "mhb_device_alloc", "mhb_memcpy_h2d", "mhb_memcpy_d2h", "mhb_spgemm_host_f64", "mhb_spgemm_host_f32", "mhb_host_alloc", "mhb_host_free",
     "mhb_form_mask_matrix_B", "mhb_get_row_info", "mhb_get_bins", "mhb_get_timing", "mhb_get_stats",
     "mhb_transpose_f64", "mhb_transpose_f32", "mhb_get_stream",
@@ -42,6 +43,7 @@ ABI_SYMBOLS = [
     "mhb_shard_offsets", "mhb_nccl_unique_id", "mhb_shard_init_nccl", "mhb_shard_broadcast",
 ]
 SHARD_BLOB_BYTES = 128
+ERR_CUDA, ERR_ARG, ERR_OVERFLOW, ERR_NOMEM, ERR_CAPACITY = 1, 2, 3, 4, 5
 
 
 class Timing(C.Structure):
@@ -62,14 +64,15 @@ class Stats(C.Structure):
     _fields_ = [("intprod", C.c_longlong), ("tileflop", C.c_longlong), ("ntiles_B", C.c_longlong),
                 ("nnzC", C.c_longlong), ("sym_bin_size", C.c_int * 24), ("num_bin_size", C.c_int * 24),
                 ("gpu_launches", C.c_int), ("hash_probes", C.c_longlong), ("sym_hash_probes", C.c_longlong),
-                ("speculative_launches", C.c_int), ("speculative_misses", C.c_int)]
+                ("speculative_launches", C.c_int), ("speculative_misses", C.c_int), ("fused_calls", C.c_int)]
 
     def as_dict(self):
         return dict(intprod=self.intprod, tileflop=self.tileflop, ntiles_B=self.ntiles_B, nnzC=self.nnzC,
                     sym_bins=dict(zip(SYM_BINS, list(self.sym_bin_size))),
                     num_bins=dict(zip(NUM_BINS, list(self.num_bin_size))), gpu_launches=self.gpu_launches,
                     hash_probes=self.hash_probes, sym_hash_probes=self.sym_hash_probes,
-                    speculative_launches=self.speculative_launches, speculative_misses=self.speculative_misses)
+                    speculative_launches=self.speculative_launches, speculative_misses=self.speculative_misses,
+                    fused_calls=self.fused_calls)
 
 
 def load_library() -> C.CDLL:
@@ -95,6 +98,10 @@ def load_library() -> C.CDLL:
     for n in ("mhb_spgemm_f64", "mhb_spgemm_f32"):
         getattr(L, n).argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, vp, vp,
                                   C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
+    for n in ("mhb_spgemm_into_f64", "mhb_spgemm_into_f32"):
+        getattr(L, n).argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, ll, C.POINTER(ll)]
+    for n in ("mhb_shard_spgemm_into_f64", "mhb_shard_spgemm_into_f32"):
+        getattr(L, n).argtypes = [vp, ip, ip, vp, vp, vp, vp, ll, C.POINTER(ll)]
     L.mhb_device_free.argtypes = [vp]
     L.mhb_device_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.mhb_memcpy_h2d.argtypes = [vp, vp, C.c_size_t]
@@ -296,6 +303,24 @@ class Tool:
     def numeric_into(self, dA_val, dB_val, dC_col, dC_val):
         f = self.L.mhb_numeric_f64 if _itemsize(dA_val) == 8 else self.L.mhb_numeric_f32
         self._chk(f(self.h, dA_val.data_ptr(), dB_val.data_ptr(), dC_col.data_ptr(), dC_val.data_ptr()))
+
+    def spgemm_into(self, M, K, N, dA_ptr, dA_col, dA_val, dB_ptr, dB_col, dB_val, dC_ptr, dC_col, dC_val) -> int:
+        """MH_spgemm into caller-owned C arrays (mhb_spgemm_into_*): one host synchronisation per
+        call in steady state.  Returns nnz(C); raises MhbError with code ERR_CAPACITY (row_ptr valid,
+        .nnzC on the exception) when dC_col / dC_val are too small."""
+        f = self.L.mhb_spgemm_into_f64 if _itemsize(dA_val) == 8 else self.L.mhb_spgemm_into_f32
+        nnz = C.c_longlong()
+        self._keep = (dA_ptr, dA_col, dB_ptr, dB_col, dC_ptr)
+        cap = min(dC_col.numel(), dC_val.numel()) if dC_col is not None else 0
+        rc = f(self.h, M, K, N, dA_col.numel(), dA_ptr.data_ptr(), dA_col.data_ptr(), dA_val.data_ptr(),
+               dB_col.numel(), dB_ptr.data_ptr(), dB_col.data_ptr(), dB_val.data_ptr(), dC_ptr.data_ptr(),
+               dC_col.data_ptr() if cap else None, dC_val.data_ptr() if cap else None, cap, C.byref(nnz))
+        if rc == ERR_CAPACITY:
+            e = MhbError(rc, self.L.mhb_last_error(self.h).decode())
+            e.nnzC = int(nnz.value)
+            raise e
+        self._chk(rc)
+        return int(nnz.value)
 
     def transpose_device(self, M, N, dA_ptr, dA_col, dA_val):
         """T = A^T on the device (mhb_transpose_*): -> (dT_ptr[N+1], dT_col[nnz], dT_val[nnz])."""

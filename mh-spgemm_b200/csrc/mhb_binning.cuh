@@ -329,6 +329,39 @@ __global__ void __launch_bounds__(256) k_classify_num(int M, const int *__restri
     }
 }
 
+// Fused call (mhb_spgemm_into_*): the numeric kernels are launched before the host has read
+// anything of this call.  This one-thread kernel, between the row-offset scan and the numeric
+// phase, verifies on the device what do_symbolic otherwise verifies on the host -- the
+// speculative symbolic launch covered the input, every populated numeric bin has a kernel coming,
+// the pool is large enough, C fits the caller's buffers -- and leaves the verdict in scal[SC_GATE].
+__global__ void k_fused_gate(int *__restrict__ scal, unsigned sym_launched, int planned_tileflop,
+                             unsigned num_launched, int planned_rownnz, long long capacity, int sb_global,
+                             int nb_global, int sb_count, int nb_count)
+{
+    pdl_prologue();
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    int g = 0;
+    if (scal[SC_SPEC_MISS])
+        g |= GATE_SYM_MISS;
+    for (int b = 1; b < sb_count; ++b) // bin 0 (rows without products) has no kernel
+        if (scal[SC_SYM_SIZE + b] > 0 && !((sym_launched >> b) & 1u))
+            g |= GATE_SYM_MISS;
+    if (scal[SC_SYM_SIZE + sb_global] > 0 && scal[SC_MAX_TILEFLOP] > planned_tileflop)
+        g |= GATE_SYM_MISS;
+    for (int b = 1; b < nb_count; ++b)
+        if (scal[SC_NUM_SIZE + b] > 0 && !((num_launched >> b) & 1u))
+            g |= GATE_NUM_MISS;
+    if (scal[SC_NUM_SIZE + nb_global] > 0 && scal[SC_MAX_ROWNNZ] > planned_rownnz)
+        g |= GATE_NUM_MISS;
+    const long long nnz = *reinterpret_cast<const long long *>(scal + SC_NNZC_LO);
+    if (nnz > capacity)
+        g |= GATE_CAPACITY;
+    if (scal[SC_ERROR] != DEVERR_NONE)
+        g |= GATE_ERROR;
+    scal[SC_GATE] = g;
+}
+
 // ---------------------------------------------------------------------------------------
 // Stable binning: count per block, scan per bin across blocks on the device, scatter with
 // warp-level ranks (match_any + popc) and a warp prefix in shared memory.

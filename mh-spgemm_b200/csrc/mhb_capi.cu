@@ -130,6 +130,12 @@ struct mhb_context
     bool spec_ok = false;                // the previous symbolic on this handle finished and left its bin sizes behind
     int spec_key[5] = {0, 0, 0, 0, 0};   // M, K, N, nnzA, nnzB of that call
     int spec_calls = 0, spec_misses = 0; // statistics (mhb_stats)
+    // fused call (mhb_spgemm_into_*): do_symbolic left its host read to the caller, who launches the
+    // numeric kernels first; the symbolic bins it launched and the pool size it planned for
+    bool fused_pending = false;
+    int fused_launched[MHB_MAX_BINS + 1] = {0};
+    int fused_planned_tileflop = 0;
+    int fused_calls = 0;
     int mask_onepass = 1;                // option "mask_onepass": one-pass mask builder (0: the round-1 five-kernel chain)
     int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
@@ -551,11 +557,18 @@ size_t hash_list_smem(int S)
 }
 
 template <typename T>
-int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv)
+int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool spec = false)
 {
+    // spec: the fused call (do_spgemm_into) has not read this call's bin sizes; h->num_off and
+    // h->max_rownnz are the previous call's and only size grids and scratch, the kernels take
+    // their ranges from the device-side offsets and stand down when the capacity gate is set
     const int *off = h->num_off;
     auto n_of = [&](int b) { return off[b + 1] - off[b]; };
     const int *bins = h->bins_num.as<int>();
+    auto list = [&](int b) {
+        return spec ? RowList{bins, h->scal.as<int>() + SC_NUM_OFF + b, -1, h->scal.as<int>() + SC_GATE}
+                    : RowList{bins + off[b], nullptr, n_of(b), nullptr};
+    };
     const int4 *arow = h->arow.as<int4>();
     int *scal = h->scal.as<int>();
     const int cap_blocks = h->num_sms * 16;
@@ -574,13 +587,13 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (threads == 0)
         {
             auto kern = k_num_hash_list<T, true>;
-            LAUNCH_ON(h, st, kern, std::min(cdiv(rows_in_bin, 4), grid_cap), 128, 4 * table, bins + off[bin], rows_in_bin,
+            LAUNCH_ON(h, st, kern, std::min(cdiv(rows_in_bin, 4), grid_cap), 128, 4 * table, list(bin),
                       Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, table, probes);
         }
         else
         {
             auto kern = k_num_hash_list<T, false>;
-            LAUNCH_ON(h, st, kern, std::min(rows_in_bin, grid_cap), threads, table, bins + off[bin], rows_in_bin, Ap, Ac,
+            LAUNCH_ON(h, st, kern, std::min(rows_in_bin, grid_cap), threads, table, list(bin), Ap, Ac,
                       Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(slots), scal, 0, probes);
         }
         return MHB_OK;
@@ -596,14 +609,14 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         // shared memory only for the sort of the compacted keys (6 B per entry + buckets)
         const int sort_smem = (int)std::min<long long>(MHB_SMEM_MAX - 1024, 7LL * h->max_rownnz + 1024);
-        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, sort_smem, bins + off[NB_H_GLOBAL], n, Ap, Ac, Av, Bp, Bc, Bv, arow,
+        LAUNCH_ON(h, st, k_num_hash_block<T>, nblk, 1024, sort_smem, list(NB_H_GLOBAL), Ap, Ac, Av, Bp, Bc, Bv, arow,
                   Cp, Cc, Cv, 0, h->pool.as<unsigned char>(), slots, scal, sort_smem, probes);
     }
     if ((n = n_of(NB_H_BLOCK_L)) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
-               bins + off[NB_H_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
+               list(NB_H_BLOCK_L), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, log2_ceil(NB_H_BLOCK_L_SLOTS),
                (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_BLOCK_L)) > 0)
@@ -611,7 +624,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         int wcap = (int)std::min<long long>(NB_WIN_BLOCK_L_COLS, (((long long)h->N + 31) / 32) * 32);
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 1024, wcap * sizeof(T) + (wcap / 32) * 8,
-               bins + off[NB_WIN_BLOCK_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+               list(NB_WIN_BLOCK_L), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
     if ((n = n_of(NB_H_BLOCK_M)) > 0)
     {
@@ -622,7 +635,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 1024, NB_H_BLOCK_L_SLOTS * (sizeof(T) + 4),
-                      bins + off[NB_H_BLOCK_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      list(NB_H_BLOCK_M), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                       log2_ceil(NB_H_BLOCK_L_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_H_BLOCK_S)) > 0)
@@ -634,7 +647,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
-                      bins + off[NB_H_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      list(NB_H_BLOCK_S), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                       log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_H_BLOCK_XS)) > 0)
@@ -647,7 +660,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks), 256, NB_H_BLOCK_S_SLOTS * (sizeof(T) + 4),
-                      bins + off[NB_H_BLOCK_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      list(NB_H_BLOCK_XS), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                       log2_ceil(NB_H_BLOCK_S_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_BLOCK_S)) > 0)
@@ -655,7 +668,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         int wcap = NB_WIN_BLOCK_S_COLS;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_win_block<T>, std::min(n, cap_blocks), 256, wcap * sizeof(T) + (wcap / 32) * 8,
-               bins + off[NB_WIN_BLOCK_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
+               list(NB_WIN_BLOCK_S), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, wcap);
     }
     if ((n = n_of(NB_H_WARP_L)) > 0)
     {
@@ -667,7 +680,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         }
         else
             LAUNCH_ON(h, st, k_num_hash_block<T>, std::min(n, cap_blocks * 4), 64, NB_H_WARP_L_SLOTS * (sizeof(T) + 4),
-                      bins + off[NB_H_WARP_L], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+                      list(NB_H_WARP_L), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                       log2_ceil(NB_H_WARP_L_SLOTS), (unsigned char *)nullptr, 0LL, scal, 0, probes);
     }
     if ((n = n_of(NB_WIN_COMPACT)) > 0)
@@ -677,7 +690,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
                             (size_t)WPB * (SB_BM_STORE_WORDS + 2 + 34) * 8;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_compact_rowtwins<T>, std::min(cdiv(cdiv(n, 3), WPB), cap_blocks), kRowTwinThreads, smem,
-                  bins + off[NB_WIN_COMPACT], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_COMPACT_MAXN,
+                  list(NB_WIN_COMPACT), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_COMPACT_MAXN,
                   h->bsame.as<unsigned char>(), h->asame, h->bm_store.as<unsigned>(), h->bm_slot.as<int>());
     }
     if ((n = n_of(NB_WIN_WARP)) > 0)
@@ -688,7 +701,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             constexpr int WPB = kRowTwinThreads / 32;
             const size_t smem = (size_t)WPB * 3 * (NB_WIN_WARP_COLS + 34) * sizeof(T) + (size_t)WPB * 34 * 8;
             LAUNCH_ON(h, st, k_num_win_rowtwins<T>, std::min(cdiv(cdiv(n, 3), WPB), cap_blocks), kRowTwinThreads, smem,
-                      bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_WARP_COLS,
+                      list(NB_WIN_WARP), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv, NB_WIN_WARP_COLS,
                       h->bsame.as<unsigned char>(), h->asame);
         }
         else
@@ -696,7 +709,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             constexpr int G = 32, GPB = kNumGroupThreads / G;
             auto kern = k_num_win_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-                      GPB * (NB_WIN_WARP_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_WARP], n, Ap, Ac, Av, Bp, Bc,
+                      GPB * (NB_WIN_WARP_COLS * sizeof(T) + (G + 2) * 16), list(NB_WIN_WARP), Ap, Ac, Av, Bp, Bc,
                       Bv, arow, Cp, Cc, Cv, NB_WIN_WARP_COLS, h->bsame.as<unsigned char>());
         }
     }
@@ -712,7 +725,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             constexpr int G = 32, GPB = kNumGroupThreads / G;
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-                      GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_M], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      GPB * NB_H_WARP_M_SLOTS * (sizeof(T) + 4), list(NB_H_WARP_M), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                       Cc, Cv, log2_ceil(NB_H_WARP_M_SLOTS), scal, probes);
         }
     }
@@ -728,7 +741,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             constexpr int G = 32, GPB = kNumGroupThreads / G;
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-                      GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_S], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      GPB * NB_H_WARP_S_SLOTS * (sizeof(T) + 4), list(NB_H_WARP_S), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                       Cc, Cv, log2_ceil(NB_H_WARP_S_SLOTS), scal, probes);
         }
     }
@@ -744,7 +757,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
             constexpr int G = 32, GPB = kNumGroupThreads / G;
             auto kern = k_num_hash_group<G, T>;
             LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-                      GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), bins + off[NB_H_WARP_XS], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
+                      GPB * NB_H_WARP_XS_SLOTS * (sizeof(T) + 4), list(NB_H_WARP_XS), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp,
                       Cc, Cv, log2_ceil(NB_H_WARP_XS_SLOTS), scal, probes);
         }
     }
@@ -754,7 +767,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_win_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * (NB_WIN_G8_COLS * sizeof(T) + (G + 2) * 16), bins + off[NB_WIN_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
+               GPB * (NB_WIN_G8_COLS * sizeof(T) + (G + 2) * 16), list(NB_WIN_G8), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc,
                Cv, NB_WIN_G8_COLS, h->bsame.as<unsigned char>());
     }
     if ((n = n_of(NB_H_G8)) > 0)
@@ -763,7 +776,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         auto kern = k_num_hash_group<G, T>;
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, kern, std::min(cdiv(n, GPB), cap_blocks), kNumGroupThreads,
-               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), bins + off[NB_H_G8], n, Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
+               GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), list(NB_H_G8), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal, probes);
     }
     if ((n = n_of(NB_TINY)) > 0)
@@ -771,7 +784,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
         if (int e_ = next_bin_stream(h, &st)) return e_;
         LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
                   NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4),
-                  bins + off[NB_TINY], n, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+                  list(NB_TINY), Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
     }
     return join_bins(h);
 }
@@ -813,9 +826,14 @@ float ev_ms(mhb_context *h, int a, int b)
     return ms;
 }
 
+int finish_symbolic(mhb_context *h, const int *hs, long long *nnzC_out);
+int prepare_a_twins(mhb_context *h);
+
 int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, int nnzB,
-                const int *Bp, const int *Bc, int *Cp, long long *nnzC_out, bool allow_spec = true)
+                const int *Bp, const int *Bc, int *Cp, long long *nnzC_out, bool allow_spec = true,
+                long long fused_capacity = -1)
 {
+    h->fused_pending = false;
     if (M < 0 || K < 0 || N < 0 || nnzA < 0 || nnzB < 0)
         return fail(h, MHB_ERR_ARG, "negative dimension");
     if (!Ap || !Bp || !Cp || (nnzA > 0 && !Ac) || (nnzB > 0 && !Bc))
@@ -925,6 +943,25 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     rc = run_scan(h, LoadInt{Cp}, M, Cp, 1, reinterpret_cast<long long *>(scal + SC_NNZC_LO));
     if (rc)
         return rc;
+    if (spec && fused_capacity >= 0)
+    {
+        // fused call: no host read here.  The verdict on this call's speculation is formed on the
+        // device (k_fused_gate) and the caller launches the numeric kernels behind it; the host reads
+        // the scalars once, after the numeric phase (finish_symbolic).
+        unsigned sym_mask = 0, num_mask = 0;
+        for (int b = 1; b < SB_COUNT; ++b)
+            sym_mask |= (launched[b + 1] > launched[b]) ? (1u << b) : 0u;
+        for (int b = 1; b < NB_COUNT; ++b)
+            num_mask |= (h->num_off[b + 1] > h->num_off[b]) ? (1u << b) : 0u;
+        LAUNCH(h, k_fused_gate, 1, 32, 0, scal, sym_mask, planned_tileflop, num_mask, h->max_rownnz,
+               std::min<long long>(fused_capacity, h->nnz_limit), (int)SB_H_GLOBAL, (int)NB_H_GLOBAL, (int)SB_COUNT,
+               (int)NB_COUNT);
+        CU(cudaEventRecord(h->ev[EV_HANDOFF], h->stream));
+        std::memcpy(h->fused_launched, launched, sizeof(launched));
+        h->fused_planned_tileflop = planned_tileflop;
+        h->fused_pending = true;
+        return MHB_OK;
+    }
     CU(cudaMemcpyAsync(hs, scal, SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaEventRecord(h->ev[EV_HANDOFF], h->stream));
     CU(cudaStreamSynchronize(h->stream)); // read #2: nnz(C) + numeric bin sizes (the hand-off)
@@ -944,6 +981,22 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
             return do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC_out, false);
         }
     }
+    rc = finish_symbolic(h, hs, nnzC_out);
+    if (rc)
+        return rc;
+    rc = prepare_a_twins(h);
+    if (rc)
+        return rc;
+    h->have_pattern = true;
+    if (h->verbose)
+        std::printf("C.nnz = %lld\n", h->nnzC); // the reference's print (src/main.cu:58), opt-in
+    return MHB_OK;
+}
+
+// The host has this call's scalar block in hs: bin sizes, nnz(C), statistics, stage times.
+int finish_symbolic(mhb_context *h, const int *hs, long long *nnzC_out)
+{
+    const int key[5] = {h->M, h->K, h->N, h->nnzA, h->nnzB};
     std::memcpy(h->sym_off, hs + SC_SYM_OFF, sizeof(h->sym_off));
     h->max_tileflop = hs[SC_MAX_TILEFLOP];
     std::memcpy(&h->stats.intprod, hs + SC_INTPROD_LO, 8);
@@ -952,6 +1005,7 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     std::memcpy(h->stats.sym_bin_size, hs + SC_SYM_SIZE, sizeof(int) * MHB_MAX_BINS);
     h->stats.speculative_launches = h->spec_calls;
     h->stats.speculative_misses = h->spec_misses;
+    h->stats.fused_calls = h->fused_calls;
     std::memcpy(h->spec_key, key, sizeof(key));
     h->spec_ok = true;
     std::memcpy(h->num_off, hs + SC_NUM_OFF, sizeof(h->num_off));
@@ -973,9 +1027,16 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     if (h->nnzC > h->nnz_limit)
         return fail(h, MHB_ERR_OVERFLOW,
                     "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the int32 CSR contract; shard the rows of A");
-    // twin rows of A (same column list as the previous row), needed only by the row-twin numeric
-    // kernels: B's flags when A is B, else compared now -- off the symbolic critical path
-    if (Ap == Bp && Ac == Bc)
+    return MHB_OK;
+}
+
+// Twin rows of A (same column list as the previous row), needed only by the row-twin numeric
+// kernels: B's flags when A is B, else compared now -- off the symbolic critical path.  Reads
+// h->num_off (in a fused call: the previous call's, like the numeric launch that follows).
+int prepare_a_twins(mhb_context *h)
+{
+    const int M = h->M;
+    if (h->Ap == h->Bp && h->Ac == h->Bc)
         h->asame = h->bsame.as<unsigned char>();
     else
     {
@@ -983,13 +1044,10 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
         const bool needed = (h->num_off[NB_WIN_COMPACT + 1] > h->num_off[NB_WIN_COMPACT]) ||
                             (h->row_twins && h->num_off[NB_WIN_WARP + 1] > h->num_off[NB_WIN_WARP]);
         if (M > 0 && needed && !h->asame_early)
-            LAUNCH(h, k_rows_same_cols, cdiv((long long)M * 8, 256), 256, 0, M, Ap, Ac,
+            LAUNCH(h, k_rows_same_cols, cdiv((long long)M * 8, 256), 256, 0, M, h->Ap, h->Ac,
                    h->asame_buf.as<unsigned char>());
         h->asame = h->asame_buf.as<unsigned char>();
     }
-    h->have_pattern = true;
-    if (h->verbose)
-        std::printf("C.nnz = %lld\n", h->nnzC); // the reference's print (src/main.cu:58), opt-in
     return MHB_OK;
 }
 
@@ -1025,6 +1083,78 @@ int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sy
             h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
     }
     return MHB_OK;
+}
+
+// The fused call: C = A*B into caller-owned C arrays of `capacity` entries.  A caller that
+// multiplies the same shapes repeatedly (the loop of src/main.cu:118-125, an AMG setup, a
+// time-stepping code) keeps its C buffers, so the hand-off of src/main.cu:55-60 -- read nnz(C),
+// allocate, continue -- has nothing left to allocate, and with it goes the last reason for the host
+// to look at the device in the middle of the pipeline.  In steady state (same shape as the previous
+// call on the handle) every kernel of both phases is launched from the previous call's bin sizes,
+// the kernels take their row ranges from the device-side offsets, a one-thread kernel checks the
+// guess on the device (k_fused_gate) and the numeric kernels stand down if it fails; the host
+// synchronises ONCE, at the end, and re-runs the ordinary two-read path on a miss.
+template <typename T>
+int do_spgemm_into(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, const T *Av, int nnzB,
+                   const int *Bp, const int *Bc, const T *Bv, int *Cp, int *Cc, T *Cv, long long capacity,
+                   long long *nnzC)
+{
+    if (!nnzC || capacity < 0 || (capacity > 0 && (!Cc || !Cv)))
+        return fail(h, MHB_ERR_ARG, "null output pointer / negative capacity");
+    if ((nnzA > 0 && !Av) || (nnzB > 0 && !Bv))
+        return fail(h, MHB_ERR_ARG, "null value pointer");
+    *nnzC = 0;
+    int rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC, true, capacity);
+    if (rc)
+        return rc;
+    if (h->fused_pending)
+    {
+        h->fused_pending = false;
+        ++h->fused_calls;
+        int *hs = h->h_scal.as<int>();
+        rc = prepare_a_twins(h);
+        if (rc)
+            return rc;
+        CU(cudaEventRecord(h->ev[EV_NUM0], h->stream));
+        rc = launch_numeric_bins<T>(h, Av, Bv, Cc, Cv, true);
+        if (rc)
+            return rc;
+        CU(cudaEventRecord(h->ev[EV_NUM1], h->stream));
+        CU(cudaMemcpyAsync(hs, h->scal.as<int>(), SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream)); // the one host read of the call
+        const int gate = hs[SC_GATE];
+        // SC_SPEC_MISS raised after the gate: a pool row of the numeric phase outgrew the planned table
+        const bool late_miss = gate == 0 && hs[SC_SPEC_MISS] != 0;
+        if ((gate & (GATE_SYM_MISS | GATE_NUM_MISS)) || late_miss)
+        {
+            ++h->spec_misses; // redo the ordinary way (below)
+            rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC, false);
+            if (rc)
+                return rc;
+        }
+        else
+        {
+            rc = check_dev_error(h, hs);
+            if (rc)
+                return rc;
+            rc = finish_symbolic(h, hs, nnzC);
+            if (rc)
+                return rc;
+            if (gate & GATE_CAPACITY)
+                return fail(h, MHB_ERR_CAPACITY, "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the capacity of the caller's C arrays (" +
+                                                     std::to_string(capacity) + "); row_ptr is valid, grow C.col / C.val and call again");
+            h->have_pattern = true;
+            h->stats.gpu_launches = h->launches;
+            std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
+            h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
+            h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
+            return MHB_OK;
+        }
+    }
+    if (*nnzC > capacity)
+        return fail(h, MHB_ERR_CAPACITY, "nnz(C) = " + std::to_string(*nnzC) + " exceeds the capacity of the caller's C arrays (" +
+                                             std::to_string(capacity) + "); row_ptr is valid, grow C.col / C.val and call again");
+    return do_numeric<T>(h, Av, Bv, Cc, Cv, true);
 }
 
 template <typename T>
@@ -1358,6 +1488,7 @@ extern "C"
             h->verbose = (int)value;
         else
             return fail(h, MHB_ERR_ARG, "unknown option " + k);
+        h->spec_ok = false; // bin sizes remembered from the previous call were formed under the old options
         return MHB_OK;
     }
 
@@ -1399,6 +1530,24 @@ extern "C"
             return MHB_ERR_ARG;
         return do_spgemm<float>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
                                 dC_col, dC_val, nnzC);
+    }
+    int mhb_spgemm_into_f64(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                            const double *dA_val, int nnzB, const int *dB_ptr, const int *dB_col, const double *dB_val,
+                            int *dC_ptr, int *dC_col, double *dC_val, long long capacity, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm_into<double>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
+                                      dC_col, dC_val, capacity, nnzC);
+    }
+    int mhb_spgemm_into_f32(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                            const float *dA_val, int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
+                            int *dC_ptr, int *dC_col, float *dC_val, long long capacity, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return do_spgemm_into<float>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
+                                     dC_col, dC_val, capacity, nnzC);
     }
     int mhb_device_free(void *dptr) { return cudaFree(dptr) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA; }
     int mhb_device_alloc(void **dptr, size_t bytes)

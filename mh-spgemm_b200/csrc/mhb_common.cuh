@@ -116,8 +116,23 @@ struct RowList
     const int *rows;
     const int *off;
     int n;
+    const int *gate; // optional (fused call): when *gate != 0 the list reads as empty and the kernel stands down
     __device__ __forceinline__ const int *begin() const { return n >= 0 ? rows : rows + off[0]; }
-    __device__ __forceinline__ int size() const { return n >= 0 ? n : off[1] - off[0]; }
+    __device__ __forceinline__ int size() const
+    {
+        if (gate && *gate)
+            return 0;
+        return n >= 0 ? n : off[1] - off[0];
+    }
+};
+
+// bits of scal[SC_GATE]
+enum GateBit
+{
+    GATE_SYM_MISS = 1, // the speculative symbolic launch did not cover this input (see do_symbolic)
+    GATE_NUM_MISS = 2, // a numeric bin is populated that the previous call did not launch, or a row outgrew the pool
+    GATE_CAPACITY = 4, // nnz(C) exceeds the caller's C.col / C.val capacity (or the int32 contract)
+    GATE_ERROR = 8,    // a symbolic kernel raised a device error
 };
 
 // error flags raised by kernels (checked by the host at the next synchronisation point)
@@ -137,13 +152,16 @@ enum Scalar
     SC_MAX_TILEFLOP = 8,
     SC_MAX_ROWNNZ = 9,
     SC_ERROR = 10,
-    SC_SPEC_MISS = 11,     // a speculative symbolic launch met a capacity it had not planned for: redo
+    SC_SPEC_MISS = 11,     // a speculative launch met a capacity it had not planned for: redo
     SC_PROBES_LO = 12,     // unsigned long long at [12..13]: failed probes of the numeric hash kernels (option count_probes)
     SC_SYM_PROBES_LO = 14, // unsigned long long at [14..15]: same for the symbolic tile hash
     SC_SYM_SIZE = 16,               // MHB_MAX_BINS ints
     SC_SYM_OFF = 40,                // MHB_MAX_BINS + 1 ints
     SC_NUM_SIZE = 72,               // MHB_MAX_BINS ints
     SC_NUM_OFF = 96,                // MHB_MAX_BINS + 1 ints
+    // fused call (mhb_spgemm_into_*): reasons why the speculatively launched numeric kernels must
+    // stand down (GateBit); written by k_fused_gate between the row-offset scan and the numeric phase
+    SC_GATE = 124,
     SC_COUNT = 128
 };
 

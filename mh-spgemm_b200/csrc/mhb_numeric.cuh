@@ -36,12 +36,14 @@ constexpr int kPre = 3;      // chunks of the next B row prefetched by the dense
 // =========================================================================================
 template <int G, typename T>
 __global__ void __launch_bounds__(kNumGroupThreads, 3) // 3 blocks/SM is what the 64 KB windows allow
-    k_num_win_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_num_win_group(RowList list, const int *__restrict__ Ap,
                     const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                     const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
                     const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int wcap,
                     const unsigned char *__restrict__ same)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int GPB = kNumGroupThreads / G;
     const int g = threadIdx.x / G, l = threadIdx.x % G;
@@ -102,12 +104,14 @@ constexpr int kRowTwinThreads = 128;
 
 template <typename T>
 __global__ void __launch_bounds__(kRowTwinThreads)
-    k_num_win_rowtwins(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_num_win_rowtwins(RowList list, const int *__restrict__ Ap,
                        const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                        const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
                        const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int wcap,
                        const unsigned char *__restrict__ bsame, const unsigned char *__restrict__ asame)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int G = 32, WPB = kRowTwinThreads / 32, SG = G + 2;
     const int warp = threadIdx.x >> 5, l = lane_id();
@@ -345,13 +349,15 @@ __device__ __forceinline__ void compact_accumulate(T *acc0, int ncap, const T *s
 // =========================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kRowTwinThreads)
-    k_num_compact_rowtwins(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_num_compact_rowtwins(RowList list, const int *__restrict__ Ap,
                            const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                            const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
                            const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int ncap,
                            const unsigned char *__restrict__ bsame, const unsigned char *__restrict__ asame,
                            const unsigned *__restrict__ bm_store, const int *__restrict__ bm_slot)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int G = 32, WPB = kRowTwinThreads / 32, SG = G + 2, LUT = SB_BM_STORE_WORDS + 2;
     const int warp = threadIdx.x >> 5, l = lane_id();
@@ -630,12 +636,14 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_tot /*32*/, int 
 // smem: acc[wcap] | flags[wcap/32] | wpre[wcap/32]
 // =========================================================================================
 template <typename T>
-__global__ void k_num_win_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+__global__ void k_num_win_block(RowList list, const int *__restrict__ Ap,
                                 const int *__restrict__ Ac, const T *__restrict__ Av,
                                 const int *__restrict__ Bp, const int *__restrict__ Bc,
                                 const T *__restrict__ Bv, const int4 *__restrict__ arow,
                                 const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int wcap)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
     T *acc = reinterpret_cast<T *>(sm_raw);
@@ -901,12 +909,14 @@ __device__ __forceinline__ bool bucket_sort_emit_block(int *keys, T *vals, int n
 // ---- hash, G lanes per row, table of 2^logS (key, value) slots per group -----------------
 template <int G, typename T>
 __global__ void __launch_bounds__(kNumGroupThreads)
-    k_num_hash_group(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+    k_num_hash_group(RowList list, const int *__restrict__ Ap,
                      const int *__restrict__ Ac, const T *__restrict__ Av, const int *__restrict__ Bp,
                      const int *__restrict__ Bc, const T *__restrict__ Bv, const int4 *__restrict__ arow,
                      const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
                      int *__restrict__ scal, unsigned long long *__restrict__ probes)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     constexpr int GPB = kNumGroupThreads / G;
     int np = 0;
@@ -1081,7 +1091,7 @@ __device__ __forceinline__ bool pool_bucket_sort_emit(const int *gkeys, const T 
 
 // ---- hash, one block per row; table in shared memory or in the global pool ---------------
 template <typename T>
-__global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+__global__ void k_num_hash_block(RowList list, const int *__restrict__ Ap,
                                  const int *__restrict__ Ac, const T *__restrict__ Av,
                                  const int *__restrict__ Bp, const int *__restrict__ Bc,
                                  const T *__restrict__ Bv, const int4 *__restrict__ arow,
@@ -1090,6 +1100,8 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
                                  long long pool_slots, int *__restrict__ scal, int sort_smem,
                                  unsigned long long *__restrict__ probes)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
     int np = 0;
@@ -1107,6 +1119,12 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
             logS = 10;
             while ((1LL << logS) < 2LL * n_row)
                 ++logS;
+            if ((1LL << logS) > pool_slots) // a speculative launch sized the pool from the previous call's largest row: redo
+            {
+                if (threadIdx.x == 0)
+                    atomicMax(scal + SC_SPEC_MISS, 1);
+                continue;
+            }
             unsigned char *base = pool + (size_t)blockIdx.x * (size_t)pool_slots * (sizeof(T) + sizeof(int));
             vals = reinterpret_cast<T *>(base);
             keys = reinterpret_cast<int *>(vals + pool_slots);
@@ -1213,13 +1231,15 @@ __global__ void k_num_hash_block(const int *__restrict__ rows, int nrows, const 
 // kernel needs.
 // smem: vals[S] | keys[S] | start[NB+1] | misc[3] | bkey[5S/8] | list[5S/8] u16 | idx[5S/8] u16
 template <typename T, bool WROWS>
-__global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash_list(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap,
+__global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash_list(RowList rowlist, const int *__restrict__ Ap,
                                 const int *__restrict__ Ac, const T *__restrict__ Av,
                                 const int *__restrict__ Bp, const int *__restrict__ Bc,
                                 const T *__restrict__ Bv, const int4 *__restrict__ arow,
                                 const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv, int logS,
                                 int *__restrict__ scal, int table_bytes, unsigned long long *__restrict__ probes)
 {
+    const int *__restrict__ rows = rowlist.begin();
+    const int nrows = rowlist.size();
     int np = 0;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
@@ -1453,10 +1473,12 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
 // warp instructions per row than the 8-lane hash kernel (profiles/r1c_tiny_rows.md).
 template <typename T>
 __global__ void __launch_bounds__(kTinyRowThreads)
-    k_num_tiny(const int *__restrict__ rows, int nrows, const int *__restrict__ Ap, const int *__restrict__ Ac,
+    k_num_tiny(RowList list, const int *__restrict__ Ap, const int *__restrict__ Ac,
                const T *__restrict__ Av, const int *__restrict__ Bp, const int *__restrict__ Bc,
                const T *__restrict__ Bv, const int *__restrict__ Cp, int *__restrict__ Cc, T *__restrict__ Cv)
 {
+    const int *__restrict__ rows = list.begin();
+    const int nrows = list.size();
     extern __shared__ __align__(16) unsigned char sm_raw[]; // vals[NB_TINY_MAX][threads] | keys[NB_TINY_MAX][threads]
     T *vals = reinterpret_cast<T *>(sm_raw);
     int *keys = reinterpret_cast<int *>(vals + NB_TINY_MAX * kTinyRowThreads);

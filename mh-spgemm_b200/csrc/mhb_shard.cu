@@ -713,6 +713,33 @@ extern "C"
         return rc;
     }
 
+    int mhb_shard_spgemm_into_f64(mhb_shard_t s, int r_lo, int r_hi, const double *dA_val, int *dC_ptr, int *dC_col,
+                                  double *dC_val, long long capacity, long long *nnzC)
+    {
+        if (!s || s->phase != 3 || s->vbytes != 8 || r_lo < 0 || r_hi < r_lo || r_hi > s->M)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_spgemm_into_f64: bad row range, incomplete plan or value type mismatch");
+        int rc = mhb_spgemm_into_f64(s->h, r_hi - r_lo, s->i1 - s->i0, s->N, s->nnzA, s->Ap + r_lo, s->Ac_local, dA_val,
+                                     (int)s->nnz_img, s->img_ptr, reinterpret_cast<const int *>(s->w2),
+                                     reinterpret_cast<const double *>(s->w2 + s->val_byte_off), dC_ptr, dC_col, dC_val,
+                                     capacity, nnzC);
+        if (rc)
+            s->err = mhb_last_error(s->h);
+        return rc;
+    }
+    int mhb_shard_spgemm_into_f32(mhb_shard_t s, int r_lo, int r_hi, const float *dA_val, int *dC_ptr, int *dC_col,
+                                  float *dC_val, long long capacity, long long *nnzC)
+    {
+        if (!s || s->phase != 3 || s->vbytes != 4 || r_lo < 0 || r_hi < r_lo || r_hi > s->M)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_spgemm_into_f32: bad row range, incomplete plan or value type mismatch");
+        int rc = mhb_spgemm_into_f32(s->h, r_hi - r_lo, s->i1 - s->i0, s->N, s->nnzA, s->Ap + r_lo, s->Ac_local, dA_val,
+                                     (int)s->nnz_img, s->img_ptr, reinterpret_cast<const int *>(s->w2),
+                                     reinterpret_cast<const float *>(s->w2 + s->val_byte_off), dC_ptr, dC_col, dC_val,
+                                     capacity, nnzC);
+        if (rc)
+            s->err = mhb_last_error(s->h);
+        return rc;
+    }
+
     int mhb_shard_post_size(mhb_shard_t s, long long nnzC_local)
     {
         if (!s || s->phase < 2 || nnzC_local < 0)

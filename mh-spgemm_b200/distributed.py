@@ -384,6 +384,23 @@ class Shard:
         f = self.L.mhb_shard_numeric_f64 if self.val_dtype.itemsize == 8 else self.L.mhb_shard_numeric_f32
         self._chk(f(self.s, dA_val.data_ptr(), dC_col.data_ptr(), dC_val.data_ptr()))
 
+    def spgemm_into(self, r_lo: int, r_hi: int, dA_val, dC_ptr, dC_col, dC_val) -> int:
+        """Fused symbolic + numeric of rows [r_lo, r_hi) into caller-owned C arrays
+        (mhb_shard_spgemm_into_*): one host synchronisation per step in steady state.  Raises
+        MhbError(code ERR_CAPACITY, .nnzC) when dC_col / dC_val are too small."""
+        from .api import ERR_CAPACITY
+        f = self.L.mhb_shard_spgemm_into_f64 if self.val_dtype.itemsize == 8 else self.L.mhb_shard_spgemm_into_f32
+        nnz = self.C.c_longlong()
+        cap = min(dC_col.numel(), dC_val.numel()) if dC_col is not None else 0
+        rc = f(self.s, r_lo, r_hi, dA_val.data_ptr(), dC_ptr.data_ptr(), dC_col.data_ptr() if cap else None,
+               dC_val.data_ptr() if cap else None, cap, self.C.byref(nnz))
+        if rc == ERR_CAPACITY:
+            e = self.MhbError(rc, self.L.mhb_shard_last_error(self.s).decode())
+            e.nnzC = int(nnz.value)
+            raise e
+        self._chk(rc)
+        return int(nnz.value)
+
     def post_size(self, nnz_local: int):
         self._chk(self.L.mhb_shard_post_size(self.s, int(nnz_local)))
 

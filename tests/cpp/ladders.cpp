@@ -46,7 +46,9 @@ int main()
                     case NB_H_WARP_S: CHECK(n <= NB_H_WARP_S_MAX && n * 8 <= NB_H_WARP_S_SLOTS * 5); break;
                     case NB_H_WARP_M: CHECK(n <= NB_H_WARP_M_MAX && n * 8 <= NB_H_WARP_M_SLOTS * 5); break;
                     case NB_H_WARP_L: CHECK(n <= NB_H_WARP_L_MAX && n * 8 <= NB_H_WARP_L_SLOTS * 5); break;
+                    case NB_H_BLOCK_XS: CHECK(n <= NB_H_BLOCK_XS_MAX && n * 8 <= NB_H_BLOCK_XS_SLOTS * 5); break;
                     case NB_H_BLOCK_S: CHECK(n <= NB_H_BLOCK_S_MAX && n * 8 <= NB_H_BLOCK_S_SLOTS * 5); break;
+                    case NB_H_BLOCK_M: CHECK(n <= NB_H_BLOCK_M_MAX && n * 8 <= NB_H_BLOCK_M_SLOTS * 5); break;
                     case NB_H_BLOCK_L: CHECK(n <= NB_H_BLOCK_L_MAX && n * 8 <= NB_H_BLOCK_L_SLOTS * 5); break;
                     case NB_H_GLOBAL: CHECK(n > NB_H_BLOCK_L_MAX); break;
                     default: CHECK(false);

@@ -637,3 +637,88 @@ def test_speculative_symbolic_launch_and_miss(orc):
     assert_matches(orc, t.spgemm_host(A2, A2), Cp2, Cc2, Cv2)
     assert t.stats["speculative_launches"] == 3
     t.release()
+
+
+def _into(t, A, B, dC, cap_arrays):
+    """mhb_spgemm_into_* on device copies of A, B; returns (nnz, C as host CSR) using dC = (ptr, col, val)."""
+    dA = [api.DeviceArray(x) for x in (A.ptr, A.col, A.val)]
+    dB = dA if B is A else [api.DeviceArray(x) for x in (B.ptr, B.col, B.val)]
+    nnz = t.spgemm_into(A.M, A.N, B.N, dA[0], dA[1], dA[2], dB[0], dB[1], dB[2], dC[0], dC[1], dC[2])
+    return nnz, CSR(A.M, B.N, dC[0].numpy()[:A.M + 1], dC[1].numpy()[:nnz], dC[2].numpy()[:nnz])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["fem", "rmat14", "poisson32", "dense_rows", "rect"])
+def test_fused_call_into_caller_buffers(orc, name, dtype):
+    """mhb_spgemm_into_*: the first call on a handle runs the ordinary two-read path, a second call of
+    the same shape runs with ONE host synchronisation (both phases launched from the previous call's
+    bin sizes, verified by the device-side gate) -- same CSR either way, also with new values."""
+    A, B = INPUTS[name]()
+    A = CSR(A.M, A.N, A.ptr, A.col, A.val.astype(dtype))
+    B = A if B is None else CSR(B.M, B.N, B.ptr, B.col, B.val.astype(dtype))
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    t = api.Tool(0)
+    cap = int(Cp[-1]) + 7
+    dC = (api.DeviceArray(np.zeros(A.M + 1, np.int32)), api.DeviceArray(np.zeros(cap, np.int32)),
+          api.DeviceArray(np.zeros(cap, dtype)))
+    nnz, C = _into(t, A, B, dC, cap)
+    assert nnz == Cp[-1] and t.stats["fused_calls"] == 0
+    assert_matches(orc, C, Cp, Cc, Cv)
+    A2 = CSR(A.M, A.N, A.ptr, A.col, (A.val * 2 - 1).astype(dtype))
+    B2 = A2 if B is A else B
+    nnz, C = _into(t, A2, B2, dC, cap)
+    st = t.stats
+    assert st["fused_calls"] == 1 and st["speculative_misses"] == 0
+    Cp2, Cc2, Cv2 = orc.spgemm(A2, B2)
+    assert_matches(orc, C, Cp2, Cc2, Cv2)
+    assert st["intprod"] == orc.intprod(A, B) and st["gpu_launches"] > 0 and t.timing.Numeric > 0
+    # pattern reuse after a fused call
+    dA2v = api.DeviceArray(A.val)
+    dBv = dA2v if B is A else api.DeviceArray(B.val)
+    t.numeric_into(dA2v, dBv, dC[1], dC[2])
+    np.testing.assert_allclose(dC[2].numpy()[:nnz], Cv, rtol=RTOL[np.dtype(dtype)] * 10, atol=0)
+    t.release()
+
+
+def test_fused_call_capacity_and_miss(orc):
+    """Too-small C arrays: MHB_ERR_CAPACITY with row_ptr and nnz valid and nothing written (ordinary and
+    fused path).  Same shape, different pattern: the device-side gate stops the numeric kernels and the
+    call is redone the ordinary way."""
+    t = api.Tool(0)
+    A1 = G.poisson2d(64)
+    Cp, Cc, Cv = orc.spgemm(A1, A1)
+    n1 = int(Cp[-1])
+    small = (api.DeviceArray(np.zeros(A1.M + 1, np.int32)), api.DeviceArray(np.full(100, -5, np.int32)),
+             api.DeviceArray(np.full(100, -5.0)))
+    for k in range(2):  # k = 0: ordinary path, k = 1: fused path with the capacity bit of the gate
+        with pytest.raises(api.MhbError) as ei:
+            _into(t, A1, A1, small, 100)
+        assert ei.value.code == api.ERR_CAPACITY and ei.value.nnzC == n1
+        assert np.array_equal(small[0].numpy().astype(np.int64), Cp)
+        assert (small[1].numpy() == -5).all() and (small[2].numpy() == -5.0).all()
+    assert t.stats["fused_calls"] == 1
+    # 100 rows of 200 nonzeros that select each other + 224 singletons: same (M, K, N, nnz) as A1
+    rng = np.random.default_rng(7)
+    rows, cols = [], []
+    for r in range(100):
+        c = np.concatenate([np.arange(100), 100 + np.sort(rng.choice(3996, 100, replace=False))])
+        rows.append(np.full(200, r)), cols.append(c)
+    rows.append(np.arange(100, 324)), cols.append(rng.integers(0, 4096, 224))
+    A2 = CSR.from_coo(4096, 4096, np.concatenate(rows), np.concatenate(cols), rng=rng)
+    assert (A2.M, A2.nnz) == (A1.M, A1.nnz)
+    Cp2, Cc2, Cv2 = orc.spgemm(A2, A2)
+    cap = max(n1, int(Cp2[-1]))
+    dC = (api.DeviceArray(np.zeros(A1.M + 1, np.int32)), api.DeviceArray(np.zeros(cap, np.int32)),
+          api.DeviceArray(np.zeros(cap)))
+    nnz, C = _into(t, A1, A1, dC, cap)
+    assert_matches(orc, C, Cp, Cc, Cv)
+    misses = t.stats["speculative_misses"]
+    nnz, C = _into(t, A2, A2, dC, cap)  # same shape, bins never populated before: gate -> redo
+    assert_matches(orc, C, Cp2, Cc2, Cv2)
+    assert t.stats["speculative_misses"] == misses + 1
+    nnz, C = _into(t, A2, A2, dC, cap)  # now fused
+    assert_matches(orc, C, Cp2, Cc2, Cv2)
+    assert t.stats["speculative_misses"] == misses + 1
+    nnz, C = _into(t, A1, A1, dC, cap)  # back: A2's big-row kernels find nothing to do
+    assert_matches(orc, C, Cp, Cc, Cv)
+    t.release()
