@@ -40,6 +40,9 @@ METRIC = "SpGEMM GFLOPS (2*intprod/s), C=A*A fp64"
 UNIT = "GFLOPS (2*intprod/s)"
 
 
+SPIN_CYCLES = 400_000  # ~0.2 ms at 1.965 GHz
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,7 +163,8 @@ def cpu_baseline(A: CSR, B: CSR, intprod: int, budget_s: float = 12.0) -> dict:
 
 
 # ---------------------------------------------------------------------------------------
-L2_NOTE = "flushed between timed steps (256 MiB written, then read back)"
+L2_NOTE = ("flushed between timed steps (256 MiB written, then read back); a 0.2 ms spin kernel between the flush and "
+           "the start event lets the host queue the step ahead of the device")
 
 # numeric bin -> the kernel that serves it (csrc/mhb_capi.cu launch_numeric_bins)
 NUM_KERNEL = {"WIN_COMPACT": "k_num_compact_rowtwins", "WIN_WARP": "k_num_win_group<32>", "WIN_G8": "k_num_win_group<8>",
@@ -421,7 +425,7 @@ def main():
     a_ptr, a_col, a_val = (torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
                            torch.from_numpy(Ablk.val).to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
+    flush_sink = torch.zeros(1, dtype=torch.int64, device=dev)
     # rows of this rank cut into slices of < 2^31 products (local int32 row_ptr per slice, int64 offsets)
     slices = [(a - r0, b - r0) for a, b in slice_rows_fast(work, r0, r1, cap=(1 << 31) - 1)] if r1 > r0 else [(0, 0)]
     mode = "single" if world == 1 else args.exchange
@@ -597,7 +601,18 @@ def main():
         # back so that L2 is left full of CLEAN lines -- after a write-only flush the step also
         # pays for draining ~126 MB of dirty lines (r2e: 0.05 ms in front of the first kernel)
         flush.fill_(k & 0xFF)
-        flush_sink.copy_(flush.view(torch.int64).sum())
+        # the sum lands in flush_sink directly: `flush_sink.copy_(x.sum())` put a copy-engine
+        # memcpy between the flush and the start event, and the first kernels behind it ran
+        # 0.03-0.06 ms long (r2k: mem_alloc 0.034 / mask 0.098 ms at N=1 against 0.006 / 0.062 ms
+        # behind the barrier kernel of the N>1 runs)
+        torch.sum(flush.view(torch.int64), dim=0, keepdim=True, out=flush_sink)
+        # ... and a ~0.2 ms spin kernel in front of the start event, so that the host has the step's
+        # launches queued before the device reaches them (nvbench's blocking kernel, by time because
+        # the call under test ends with its own synchronisation).  Without it the first kernels of a
+        # step wait for the HOST, which comes out of the previous step's synchronisation and the
+        # Python around it just in time (r2k/r2l: mem_alloc 0.035 ms for a 3 us kernel, mask build
+        # 0.10 ms against 0.062 ms behind the peer barrier of the N>1 runs)
+        torch.cuda._sleep(SPIN_CYCLES)
         if mode == "peer":
             sh.barrier()       # ranks leave the flush together: no start-time skew inside the event pair
         ev[k][0].record(stream)

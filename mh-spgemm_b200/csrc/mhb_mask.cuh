@@ -238,7 +238,7 @@ __device__ __forceinline__ long long chained_scan_lookback(unsigned long long *s
 
 // ctrl[0] = chunk ticket counter (zeroed with the scalars); status[nchunks] zeroed likewise;
 // flags[] holds the row-start bits on entry and the complete tile-start flags on exit.
-__global__ void __launch_bounds__(kMaskThreads, 5)
+__global__ void __launch_bounds__(kMaskThreads, 4)
     k_mask_build(const int *__restrict__ Bc, long long nnz, long long nwords, unsigned *flags,
                  int *__restrict__ wordprefix, int *__restrict__ tilecol, unsigned *__restrict__ tilemask,
                  unsigned *__restrict__ ctrl, unsigned long long *__restrict__ status, int nchunks,
@@ -288,6 +288,39 @@ __global__ void __launch_bounds__(kMaskThreads, 5)
         if (i < WPW)
             tiles += __popc(f[i]);
     }
+    // The masks are formed BEFORE the look-back (they need no global position), so that the shuffle
+    // work of this chunk overlaps the latency of its predecessors' status words; behind the
+    // look-back only the stores are left.
+    // Mask of every run that STARTS in word i: segmented suffix-OR inside the word.  (A match_any +
+    // redux.or formulation was measured and lost -- 44 -> 54 us on the cant-like input, 36 -> 121 us
+    // on the R-MAT where every lane is its own run: MATCH.ANY takes one round per distinct value.)
+    unsigned m[WPW];
+#pragma unroll
+    for (int i = 0; i < WPW; ++i)
+    {
+        const unsigned fi = f[i];
+        unsigned bits = (c[i] >= 0) ? (1u << (c[i] & 31)) : 0u;
+        const unsigned above = (lane == 31) ? 0u : (fi >> (lane + 1));
+        const int seg_end = above ? lane + __ffs(above) - 1 : 31; // last lane of this lane's run inside the word
+        // step d is needed only while some run of the word is longer than d (warp-uniform test on
+        // the flag word: z has bit l set when lanes l .. l+d all belong to one run)
+        unsigned z = ~fi >> 1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            if (z == 0)
+                break;
+            const unsigned v = __shfl_down_sync(kFull, bits, d);
+            if (lane + d <= seg_end)
+                bits |= v;
+            z &= z >> d;
+        }
+        // ... plus the run's continuation in the leading lanes of the next word
+        const unsigned fn = f[i + 1];
+        const int lead = fn ? __ffs(fn) - 1 : 32;
+        const unsigned ext = (lead == 0) ? 0u : __reduce_or_sync(kFull, (lane < lead && c[i + 1] >= 0) ? (1u << (c[i + 1] & 31)) : 0u);
+        m[i] = (seg_end == 31) ? (bits | ext) : bits;
+    }
     // chunk aggregate -> look-back -> tile index in front of every word
     if (lane == 0)
         sh_warp[warp] = tiles;
@@ -316,30 +349,11 @@ __global__ void __launch_bounds__(kMaskThreads, 5)
             flags[word] = fi;
             wordprefix[word] = (int)run;
         }
-        // mask of every run that STARTS in this word: segmented suffix-OR inside the word.  (A
-        // match_any + redux.or formulation was measured and lost -- 44 -> 54 us on the cant-like
-        // input, 36 -> 121 us on the R-MAT where every lane is its own run: MATCH.ANY takes one
-        // round per distinct value.  profiles/r2_launches_F.md)
-        const bool valid = c[i] >= 0;
-        unsigned bits = valid ? (1u << (c[i] & 31)) : 0u;
-        const unsigned above = (lane == 31) ? 0u : (fi >> (lane + 1));
-        const int seg_end = above ? lane + __ffs(above) - 1 : 31; // last lane of this lane's run inside the word
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const unsigned v = __shfl_down_sync(kFull, bits, d);
-            if (lane + d <= seg_end)
-                bits |= v;
-        }
-        // ... plus the run's continuation in the leading lanes of the next word
-        const unsigned fn = f[i + 1];
-        const int lead = fn ? __ffs(fn) - 1 : 32;
-        const unsigned ext = __reduce_or_sync(kFull, (lane < lead && c[i + 1] >= 0) ? (1u << (c[i + 1] & 31)) : 0u);
-        if (valid && ((fi >> lane) & 1u))
+        if (c[i] >= 0 && ((fi >> lane) & 1u))
         {
             const int t = (int)run + __popc(fi & lanemask_lt());
             tilecol[t] = c[i] >> MHB_TILE_SHIFT;
-            tilemask[t] = (seg_end == 31) ? (bits | ext) : bits;
+            tilemask[t] = m[i];
         }
         run += __popc(fi);
     }
