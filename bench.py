@@ -172,7 +172,7 @@ NUM_KERNEL = {"WIN_COMPACT": "k_num_compact_rowtwins", "WIN_WARP": "k_num_win_gr
               "H_WARP_XS": "k_num_hash_list<wrows>", "H_WARP_S": "k_num_hash_list<wrows>", "H_WARP_M": "k_num_hash_list",
               "H_WARP_L": "k_num_hash_list", "H_BLOCK_S": "k_num_hash_list", "H_BLOCK_M": "k_num_hash_list", "H_BLOCK_XS": "k_num_hash_list",
               "H_BLOCK_L": "k_num_hash_block",
-              "H_GLOBAL": "k_num_hash_block(pool)", "TINY": "k_num_tiny"}
+              "H_GLOBAL": "k_num_hash_block(pool)", "TINY": "k_num_tiny", "TINY_S": "k_num_tiny", "TINY_M": "k_num_tiny"}
 
 
 def captured_traffic(workload: str, world: int):
@@ -419,7 +419,11 @@ def main():
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     Ablk = A.rows(r0, r1)
     tool = api.Tool(local)
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the flush, the events and the library's kernels.  (Until r2m
+    # the handle was "bound" to torch's default stream, whose handle 0 the C ABI reads as "own
+    # stream": the first kernels of a step then overlapped the tail of the L2 flush.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     tool.set_stream(stream.cuda_stream)
     dt = torch.float64
     a_ptr, a_col, a_val = (torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),

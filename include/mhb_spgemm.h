@@ -73,7 +73,8 @@ typedef struct mhb_stats {
 int mhb_create(mhb_handle_t *out, int device);
 int mhb_destroy(mhb_handle_t h);
 const char *mhb_last_error(mhb_handle_t h);
-/* cudaStream_t to run on; NULL selects the handle-owned non-blocking stream. */
+/* cudaStream_t to run on; NULL selects the handle-owned non-blocking stream (to run on the
+ * default stream pass cudaStreamLegacy or cudaStreamPerThread, not 0). */
 int mhb_set_stream(mhb_handle_t h, void *cuda_stream);
 /* Tuning / test knobs: "force_sym_path", "force_num_path" (0 auto, 1 window/bitmap only
  * where it fits, 2 hash only), "serial_bins" (1: per-bin kernels on one stream),

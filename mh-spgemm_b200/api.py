@@ -24,9 +24,10 @@ from .csr import CSR
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
-SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY"]
+SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M", "H_BLOCK_XS"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M", "H_BLOCK_XS",
+            "TINY_S", "TINY_M"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -223,7 +224,18 @@ class Tool:
         self._chk(self.L.mhb_set_option(self.h, key.encode(), int(value)))
 
     def set_stream(self, cuda_stream_ptr: int | None):
-        self._chk(self.L.mhb_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+        """None -> the handle's own non-blocking stream; an integer -> that cudaStream_t.  0 is the
+        legacy default stream (what ``torch.cuda.current_stream().cuda_stream`` returns when no other
+        stream was made current): it is passed on as cudaStreamLegacy, because a NULL pointer means
+        "own stream" in the C ABI -- before this distinction, binding to torch's default stream
+        silently left the handle on its own stream, unordered against the caller's work."""
+        if cuda_stream_ptr is None:
+            p = 0
+        elif int(cuda_stream_ptr) == 0:
+            p = 1  # cudaStreamLegacy
+        else:
+            p = int(cuda_stream_ptr)
+        self._chk(self.L.mhb_set_stream(self.h, C.c_void_p(p)))
 
     def pin(self, A: CSR) -> PinnedCSR:
         return PinnedCSR(self.L, A)

@@ -539,12 +539,13 @@ int launch_symbolic_bins(mhb_context *h, bool spec)
                SB_BM_G8_WORDS, h->bsame.as<unsigned char>(), h->have_bm_store ? h->bm_store.as<unsigned>() : nullptr,
                h->have_bm_store ? h->bm_slot.as<int>() : nullptr, a_twins, n, scal);
     }
-    if ((n = n_of(SB_TINY)) > 0)
-    {
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, list(SB_TINY),
-                  h->Ap, h->Ac, tp, tc, tm, counts);
-    }
+    for (int tb : {(int)SB_TINY, (int)SB_TINY_M, (int)SB_TINY_S}) // the same kernel per cost class
+        if ((n = n_of(tb)) > 0)
+        {
+            if (int e_ = next_bin_stream(h, &st)) return e_;
+            LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, list(tb),
+                      h->Ap, h->Ac, tp, tc, tm, counts);
+        }
     return join_bins(h);
 }
 
@@ -779,13 +780,14 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
                GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), list(NB_H_G8), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal, probes);
     }
-    if ((n = n_of(NB_TINY)) > 0)
-    {
-        if (int e_ = next_bin_stream(h, &st)) return e_;
-        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
-                  NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4),
-                  list(NB_TINY), Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
-    }
+    for (int tb : {(int)NB_TINY, (int)NB_TINY_M, (int)NB_TINY_S}) // the same kernel per cost class
+        if ((n = n_of(tb)) > 0)
+        {
+            if (int e_ = next_bin_stream(h, &st)) return e_;
+            LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
+                      NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4),
+                      list(tb), Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+        }
     return join_bins(h);
 }
 

@@ -29,6 +29,9 @@ enum MhbSymBin
     SB_H_BLOCK_L,   // tile hash, block/row,   ub <= 12288 (16384 slots)
     SB_H_GLOBAL,    // tile hash in global memory
     SB_TINY,        // one thread per row, tile list in shared memory, tile-flop <= 24
+    SB_TINY_S,      // the same kernel on the rows with tile-flop <= 4 ...
+    SB_TINY_M,      // ... and <= 12: threads of one warp then carry rows of similar cost (on power-law
+                    // inputs the rows of one bin differ 100x and a warp ran 4 of its 32 lanes, r2l)
     SB_COUNT
 };
 #define SB_BM_G8_WORDS 64
@@ -43,6 +46,8 @@ enum MhbSymBin
 #define SB_H_BLOCK_L_SLOTS 16384
 #define SB_H_BLOCK_L_MAX 12288
 #define SB_TINY_MAX 24
+#define SB_TINY_S_MAX 4
+#define SB_TINY_M_MAX 12
 #define SB_BITMAP_WORK_FACTOR 8 // bitmap when Wt <= 8 * tile-flop (or Wt <= 64)
 
 // ---- numeric bins (family 4). W = column span of the C row, n = nnz of the C row ----
@@ -66,6 +71,8 @@ enum MhbNumBin
                     // up to three twin rows of A per warp
     NB_H_BLOCK_M,   // hash, block/row,   n <= 5120 (8192 slots, claim list)
     NB_H_BLOCK_XS,  // hash, block/row,   n <= 1280 (2048 slots, claim list, 128 threads)
+    NB_TINY_S,      // NB_TINY's kernel on the rows with <= 8 products ...
+    NB_TINY_M,      // ... and <= 32 products (see SB_TINY_S)
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256
@@ -94,6 +101,8 @@ enum MhbNumBin
 #define SB_BM_STORE_WORDS 64 // stride of a stored symbolic bitmap (the SB_BM_G8 bin)
 #define NB_TINY_MAX 24
 #define NB_TINY_PRODUCTS 128
+#define NB_TINY_S_PRODUCTS 8
+#define NB_TINY_M_PRODUCTS 32
 #define NB_WINDOW_WORK_FACTOR 32 // window when W <= 32 * n (or W <= 64)
 
 // path forcing (mhb_set_option "force_sym_path"/"force_num_path")
@@ -113,7 +122,7 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
     if (ip <= 0)
         return SB_EMPTY;
     if (force == MHB_PATH_AUTO && tf <= SB_TINY_MAX)
-        return SB_TINY;
+        return tf <= SB_TINY_S_MAX ? SB_TINY_S : (tf <= SB_TINY_M_MAX ? SB_TINY_M : SB_TINY);
     long long wt = (long long)(cmax >> MHB_TILE_SHIFT) - (cmin >> MHB_TILE_SHIFT) + 1;
     bool fits = wt <= SB_BM_BLOCK_WORDS;
     bool dense = fits && (wt <= SB_BM_G8_WORDS || wt <= (long long)SB_BITMAP_WORK_FACTOR * tf);
@@ -143,7 +152,7 @@ MHB_HD int mhb_classify_num(int n, int ip, int cmin, int cmax, int force, int tf
     if (n <= 0)
         return NB_EMPTY;
     if (force == MHB_PATH_AUTO && n <= NB_TINY_MAX && ip <= NB_TINY_PRODUCTS)
-        return NB_TINY;
+        return ip <= NB_TINY_S_PRODUCTS ? NB_TINY_S : (ip <= NB_TINY_M_PRODUCTS ? NB_TINY_M : NB_TINY);
     long long w = (long long)cmax - cmin + 1;
     bool fits = w <= NB_WIN_BLOCK_L_COLS;
     bool dense = fits && (w <= 64 || w <= (long long)NB_WINDOW_WORK_FACTOR * n);

@@ -1287,6 +1287,19 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
             misc[0] = 0;
         bar();
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
+        // A row whose nnz equals its product count has no two products on one column: nothing to
+        // find, nothing to add up.  Its products go straight into the front of the table arrays in
+        // expansion order (keys[pos], vals[pos]) -- no hashing, no CAS, no claim list -- and only the
+        // sort below is left.  On power-law graphs that is most rows (webbase-like input: 94 % of the
+        // rows of these bins, 57 % of all products).
+        const bool uniq = info.x == n;
+        if (uniq)
+            walk_flat_indexed<32, T, T>(kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv, [&](int pos, int c, T v, T a) {
+                keys[pos] = c;
+                vals[pos] = a * v;
+                atomicAdd(&start[(c - cmin) >> sh], 1);
+            });
+        else
         walk_flat_post<32, T, T>(
             kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv,
             [&](int c, T v, T a) {
@@ -1389,7 +1402,7 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         {
             for (int i = tid; i < n; i += nthr)
             {
-                const unsigned short sl = list[i];
+                const unsigned short sl = uniq ? (unsigned short)i : list[i];
                 const int k = keys[sl];
                 const int pos = atomicAdd(&start[(k - cmin) >> sh], 1); // start[b] ends as the END of bucket b
                 idx[pos] = sl;
@@ -1426,7 +1439,7 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
                 rv[j] = T(0);
                 if (i < n)
                 {
-                    const int sl = list[i];
+                    const int sl = uniq ? i : (int)list[i];
                     rk[j] = keys[sl];
                     rv[j] = vals[sl];
                 }

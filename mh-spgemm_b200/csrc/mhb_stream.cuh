@@ -309,6 +309,54 @@ __device__ __forceinline__ void walk_flat(unsigned gm, int l, int s, int e, int 
     }
 }
 
+// walk_flat that also tells every product its position in the row's expansion order (products of
+// the row's first nonzero of A first, each B row front to back): update(pos, c, v, a).
+template <int G, typename TA, typename TB, class Update>
+__device__ __forceinline__ void walk_flat_indexed(unsigned gm, int l, int s, int e, int tpart, int tparts,
+                                                  const int *__restrict__ Ac, const TA *__restrict__ Av,
+                                                  const int *__restrict__ Bp, const int *__restrict__ Bc,
+                                                  const TB *__restrict__ Bv, Update update)
+{
+    int bs, be, nbs, nbe;
+    TA av, nav;
+    int rowbase = 0;
+    load_meta<TA>(s + l, e, Ac, Av, Bp, bs, be, av);
+    for (int j0 = s; j0 < e; j0 += G)
+    {
+        load_meta<TA>(j0 + G + l, e, Ac, Av, Bp, nbs, nbe, nav);
+        const int len = be - bs;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1)
+        {
+            const int t = __shfl_up_sync(gm, incl, o, G);
+            if (l >= o)
+                incl += t;
+        }
+        const int off = incl - len;
+        const int total = __shfl_sync(gm, incl, G - 1, G);
+        const int base = bs - off;
+        for (int t0 = tpart * G; t0 < total; t0 += tparts * G)
+        {
+            const int t = t0 + l;
+            int ent = 0;
+#pragma unroll
+            for (int step = G / 2; step > 0; step >>= 1)
+            {
+                const int o = __shfl_sync(gm, off, ent + step, G);
+                if (o <= t)
+                    ent += step;
+            }
+            const int q = t + __shfl_sync(gm, base, ent, G);
+            const TA a = group_bcast<TA>(gm, av, ent, G);
+            if (t < total)
+                update(rowbase + t, __ldg(&Bc[q]), __ldg(&Bv[q]), a);
+        }
+        rowbase += total;
+        bs = nbs, be = nbe, av = nav;
+    }
+}
+
 // walk_flat with convergent hooks: update(c, v, a) is executed by ALL lanes of the group
 // (c = -1 for lanes that have no product in this step) and returns an int per product (e.g. a
 // newly claimed hash slot, or -1); post(r) follows, also convergent, so both may use

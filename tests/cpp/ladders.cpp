@@ -35,7 +35,9 @@ int main()
                     CHECK(b > NB_EMPTY && b < NB_COUNT);
                     switch (b)
                     {
-                    case NB_TINY: CHECK(force == 0 && n <= NB_TINY_MAX && ip <= NB_TINY_PRODUCTS); break;
+                    case NB_TINY: CHECK(force == 0 && n <= NB_TINY_MAX && ip <= NB_TINY_PRODUCTS && ip > NB_TINY_M_PRODUCTS); break;
+                    case NB_TINY_M: CHECK(force == 0 && n <= NB_TINY_MAX && ip <= NB_TINY_M_PRODUCTS && ip > NB_TINY_S_PRODUCTS); break;
+                    case NB_TINY_S: CHECK(force == 0 && n <= NB_TINY_MAX && ip <= NB_TINY_S_PRODUCTS); break;
                     case NB_WIN_G8: CHECK(w <= NB_WIN_G8_COLS); break;
                     case NB_WIN_WARP: CHECK(w <= NB_WIN_WARP_COLS); break;
                     case NB_WIN_COMPACT: CHECK(w <= NB_WIN_WARP_COLS && n <= NB_WIN_COMPACT_MAXN); break;
@@ -54,7 +56,7 @@ int main()
                     default: CHECK(false);
                     }
                     if (force == 2)
-                        CHECK(b >= NB_H_G8 && b != NB_WIN_COMPACT && b != NB_TINY && b != NB_WIN_G8 && b != NB_WIN_WARP &&
+                        CHECK(b >= NB_H_G8 && b != NB_WIN_COMPACT && b != NB_TINY && b != NB_TINY_S && b != NB_TINY_M && b != NB_WIN_G8 && b != NB_WIN_WARP &&
                               b != NB_WIN_BLOCK_S && b != NB_WIN_BLOCK_L);
                     // symbolic: tile-flop tf = ip, words spanned wt
                     const int sb = mhb_classify_sym(ip, ip, cmin, cmax, force);
@@ -63,7 +65,9 @@ int main()
                     CHECK(sb > SB_EMPTY && sb < SB_COUNT);
                     switch (sb)
                     {
-                    case SB_TINY: CHECK(force == 0 && ip <= SB_TINY_MAX); break;
+                    case SB_TINY: CHECK(force == 0 && ip <= SB_TINY_MAX && ip > SB_TINY_M_MAX); break;
+                    case SB_TINY_M: CHECK(force == 0 && ip <= SB_TINY_M_MAX && ip > SB_TINY_S_MAX); break;
+                    case SB_TINY_S: CHECK(force == 0 && ip <= SB_TINY_S_MAX); break;
                     case SB_BM_G8: CHECK(wt <= SB_BM_G8_WORDS); break;
                     case SB_BM_WARP: CHECK(wt <= SB_BM_WARP_WORDS); break;
                     case SB_BM_BLOCK: CHECK(wt <= SB_BM_BLOCK_WORDS && wt * 4 <= MHB_SMEM_MAX); break;
