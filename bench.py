@@ -57,6 +57,9 @@ def make_workload(name: str, scale: int = 1) -> tuple[CSR, dict]:
     if name == "F":
         A = G.fem3d(8, 8, 325 * scale, 3, seed=1)
         desc = f"configs[1] cant-like FEM 27-pt 8x8x{325 * scale} x3dof, C=A*A"
+    elif name == "FP":
+        A = G.fem3d_perturbed(8, 8, 325 * scale, 3, drop=0.10, seed=1)
+        desc = f"cant-like FEM 27-pt 8x8x{325 * scale} x3dof with 10 % of the off-diagonal entries dropped at random, C=A*A"
     elif name == "P":
         n = int(os.environ.get("MHB_POISSON_N", "256"))
         A = G.poisson2d(n)
@@ -283,6 +286,46 @@ def check_slice_invariants(torch, Aslice, B, cp, cc, cv) -> dict:
     return {"sorted_in_range": ok_sorted, "rowsum_max_rel_err": err}
 
 
+def perturbed_fem(tool, torch, dev, steps=10) -> dict:
+    """The headline shape without its regularity, next to the headline number: the cant-like
+    matrix with 10 % of its off-diagonal entries dropped at random (the dof rows of a node stop
+    being exact twins).  Same call, same flush and event timing as the main loop, fewer steps;
+    structure and values checked against the host oracle."""
+    from oracle import Oracle
+    A, cfg = make_workload("FP")
+    ip = int(np.diff(A.ptr).astype(np.int64)[A.col].sum())
+    a_ptr, a_col, a_val = (torch.from_numpy(x).to(dev) for x in (A.ptr, A.col, A.val))
+    cp = torch.empty(A.M + 1, dtype=torch.int32, device=dev)
+    orc = Oracle()
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    cc = torch.empty(int(Cp[-1]), dtype=torch.int32, device=dev)
+    cv = torch.empty(int(Cp[-1]), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sink = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    ms = []
+    for k in range(3 + steps):
+        flush.fill_(k & 0xFF)
+        torch.sum(flush.view(torch.int64), dim=0, keepdim=True, out=sink)
+        torch.cuda._sleep(SPIN_CYCLES)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nnz = tool.spgemm_into(A.M, A.N, A.N, a_ptr, a_col, a_val, a_ptr, a_col, a_val, cp, cc, cv)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if k >= 3:
+            ms.append(e0.elapsed_time(e1))
+    t = float(np.mean(ms))
+    st = tool.stats
+    ok = (nnz == int(Cp[-1]) and np.array_equal(cp.cpu().numpy().astype(np.int64), Cp)
+          and np.array_equal(cc.cpu().numpy(), Cc))
+    bad, _ = orc.compare(A.M, (Cp, Cc, cv.cpu().numpy()), (Cp, Cc, Cv), 1e-12) if ok else (-1, None)
+    return {"workload": cfg["workload"], "rows": A.M, "nnzA": A.nnz, "intprod": ip, "nnzC": int(nnz),
+            "ms_per_step": round(t, 4), "gflops": round(2.0 * ip / t / 1e6, 1), "numeric_ms": round(tool.timing.Numeric, 4),
+            "parity": "bit-exact structure, values 1e-12" if ok and bad == 0 else "FAILED",
+            "num_bins": {k: v for k, v in st["num_bins"].items() if v}}
+
+
 def suite_breadth(tool, budget_s=150.0) -> dict:
     """BASELINE configs[3] in one number: C = A*A on the twelve small suite analogs, ours
     (device time, mask build included, median of 3) vs the reference's kernels on the same box
@@ -352,10 +395,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="F", choices=["F", "P", "R", "G"])
+    ap.add_argument("--workload", default="F", choices=["F", "FP", "P", "R", "G"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suite", action="store_true", help="skip the 12-matrix breadth check (N=1, workload F only)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-perturbed", action="store_true", help="skip the perturbed-FEM side measurement (N=1, workload F)")
     ap.add_argument("--contract", default="fused", choices=["fused", "two-phase"],
                     help="'fused' = mhb_spgemm_into_* (C arrays kept by the caller, one host synchronisation per "
                          "SpGEMM); 'two-phase' = mhb_symbolic, then mhb_numeric_* (the reference's hand-off as two calls)")
@@ -439,12 +483,21 @@ def main():
 
     c_buf = {}  # the caller's C arrays, kept across steps and regrown only when a slice needs more room
 
-    def multiply(into):
-        """One SpGEMM per slice into the caller's C arrays; returns the last slice and the rank's nnz.
+    def grow(buf, nnz):
+        buf[1] = buf[2] = None
+        buf[1] = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        buf[2] = torch.empty(max(nnz, 1), dtype=dt, device=dev)
+
+    def multiply(into, begin=None, end=None):
+        """One SpGEMM per slice into the caller's C arrays.  Queues the work and returns fin(), which
+        waits for it and gives (last slice, the rank's nnz).
         C.ptr / C.col / C.val are caller-owned (the hand-off of src/main.cu:55-60): a caller that
         multiplies repeatedly keeps its buffers, so they are allocated on the first step (and
         whenever nnz outgrows them: the call reports MHB_ERR_CAPACITY with the size it needs) and
-        reused afterwards; with one slice per rank nothing is shared between slices."""
+        reused afterwards; with one slice per rank nothing is shared between slices.
+        With begin / end (the two halves of the fused call) the last slice is only QUEUED here, so
+        that the caller's stop event lands right behind the last kernel instead of behind the
+        host's wake-up from the call's final synchronisation."""
         total, last = 0, None
         for i, (s0, s1) in enumerate(slices):
             key = i if len(slices) == 1 else 0  # many slices (C beyond int32): one set of buffers, reused in turn
@@ -452,18 +505,29 @@ def main():
                 c_buf[key] = [torch.empty(s1 - s0 + 1, dtype=torch.int32, device=dev), None, None]
             buf = c_buf[key]
             cp = buf[0][:s1 - s0 + 1]
+            if begin is not None and i == len(slices) - 1 and buf[1] is not None:
+                begin(s0, s1, cp, buf[1], buf[2])
+
+                def fin(total=total, s0=s0, s1=s1, cp=cp, buf=buf):
+                    try:
+                        nnz = end()
+                    except api.MhbError as e:
+                        if e.code != api.ERR_CAPACITY:
+                            raise
+                        grow(buf, e.nnzC)
+                        nnz = into(s0, s1, cp, buf[1], buf[2])
+                    return (s0, s1, cp, buf[1][:nnz], buf[2][:nnz]), total + nnz
+                return fin
             try:
                 nnz = into(s0, s1, cp, buf[1], buf[2])
             except api.MhbError as e:
                 if e.code != api.ERR_CAPACITY:
                     raise
-                buf[1] = buf[2] = None
-                buf[1] = torch.empty(max(e.nnzC, 1), dtype=torch.int32, device=dev)
-                buf[2] = torch.empty(max(e.nnzC, 1), dtype=dt, device=dev)
+                grow(buf, e.nnzC)
                 nnz = into(s0, s1, cp, buf[1], buf[2])
             total += nnz
             last = (s0, s1, cp, buf[1][:nnz], buf[2][:nnz])
-        return last, total
+        return lambda: (last, total)
 
     def two_phase(sym, num):
         """The reference's contract as two calls (symbolic -> caller sizes C -> numeric), behind the
@@ -479,17 +543,25 @@ def main():
         return into
 
     fused = args.contract == "fused"
+    # step_queue() puts one step on the stream and returns fin(), which waits for it and gives
+    # (last slice, the rank's nnz).  With the fused contract the stop event of a timed step is
+    # recorded between the two, i.e. right behind the last kernel (device_bracket = True).
+    device_bracket = fused and mode in ("single", "peer")
     if mode == "single":
         if fused:
             into = lambda s0, s1, cp, cc, cv: tool.spgemm_into(s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_val, a_ptr, a_col,
                                                                a_val, cp, cc, cv)
+            begin = lambda s0, s1, cp, cc, cv: tool.spgemm_into_begin(s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_val, a_ptr,
+                                                                      a_col, a_val, cp, cc, cv)
+            end = tool.spgemm_into_end
         else:
             into = two_phase(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, a_ptr,
                                                                    a_col, cp),
                              lambda cc, cv: tool.numeric_into(a_val, a_val, cc, cv))
+            begin = end = None
 
-        def one_step():  # B = A: one copy on the device, aliasing visible to the library
-            return multiply(into)
+        def step_queue():  # B = A: one copy on the device, aliasing visible to the library
+            return multiply(into, begin, end)
     elif mode == "peer":
         Bown = B.rows(r0, r1)  # B = A is sharded like A
         dBp = torch.from_numpy(Bown.ptr).to(dev)
@@ -502,10 +574,16 @@ def main():
         trace = []  # MHB_BENCH_TRACE=1: device time of exchange / multiply / size post per step
         if fused:
             into = lambda s0, s1, cp, cc, cv: sh.spgemm_into(s0, s1, a_val, cp, cc, cv)
+            begin = lambda s0, s1, cp, cc, cv: sh.spgemm_into_begin(s0, s1, a_val, cp, cc, cv)
+            end = sh.spgemm_into_end
         else:
             into = two_phase(lambda s0, s1, cp: sh.symbolic(s0, s1, cp), lambda cc, cv: sh.numeric_into(a_val, cc, cv))
+            begin = end = None
+        # one slice per rank: the slice size is posted to the peers from the device, behind the
+        # SpGEMM's kernels and inside the timed region, and confirmed from the host afterwards
+        device_post = fused and len(slices) == 1
 
-        def one_step():
+        def step_queue():
             tr = os.environ.get("MHB_BENCH_TRACE") == "1"
             if tr:
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -513,14 +591,24 @@ def main():
             sh.exchange()
             if tr:
                 e[1].record(stream)
-            last, total = multiply(into)
+            fin = multiply(into, begin, end)
             if tr:
                 e[2].record(stream)
-            sh.post_size(total)
+            queued = device_post and c_buf.get(0, [None, None])[1] is not None
+            if queued:
+                sh.post_size(-1)
             if tr:
                 e[3].record(stream)
                 trace.append(e)
-            return last, total
+
+            def finish():
+                last, total = fin()
+                if queued:
+                    sh.repost_size(total)
+                else:
+                    sh.post_size(total)
+                return last, total
+            return finish
     elif mode == "broadcast":
         sh = Shard(tool, rank, world, B.M, B.N, np.float64, bounds)
         sh.init_nccl()
@@ -536,11 +624,11 @@ def main():
             into = two_phase(lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, B.M, B.N, a_ptr[s0:], a_col, bp, bc, cp),
                              lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv))
 
-        def one_step():
+        def step_queue():
             sh.broadcast(Bbuf, Bbuf.numel(), 0)  # ncclBroadcast issued from C++ on the Tool's stream
-            last, total = multiply(into)
+            last, total = multiply(into)()
             sizes.gather(total)
-            return last, total
+            return lambda: (last, total)
     else:  # sendrecv: the round-1 exchange (torch.distributed grouped send/recv), kept as the fallback
         kr = [column_range(A.rows(int(bounds[r]), int(bounds[r + 1]))) for r in range(world)]
         plan = RangeExchange(rank, world, bounds, kr, B.ptr, dt, dev)
@@ -555,14 +643,17 @@ def main():
             own_col, own_val = a_col, a_val
         sizes = SliceSizes(rank, world, dev)
 
-        def one_step():
+        def step_queue():
             bp, bc, bv = plan.run(own_col, own_val)
             last, total = multiply(two_phase(
                 lambda s0, s1, cp: tool_symbolic_into(tool, s1 - s0, plan.K_local, B.N, a_ptr[s0:], a_shift, bp,
                                                       bc[:plan.nnz_local], cp),
-                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv)))
+                lambda cc, cv: tool.numeric_into(a_val, bv, cc, cv)))()
             sizes.gather(total)
-            return last, total
+            return lambda: (last, total)
+
+    def one_step():
+        return step_queue()()
 
     def totals():
         if mode == "single":
@@ -620,8 +711,12 @@ def main():
         if mode == "peer":
             sh.barrier()       # ranks leave the flush together: no start-time skew inside the event pair
         ev[k][0].record(stream)
-        last, nnz_local = one_step()
-        ev[k][1].record(stream)
+        fin = step_queue()
+        if device_bracket:
+            ev[k][1].record(stream)  # behind the last kernel of the step; fin() waits for it
+        last, nnz_local = fin()
+        if not device_bracket:
+            ev[k][1].record(stream)
         num_ms.append(tool.timing.Numeric)
         launches += tool.stats["gpu_launches"] * len(slices) + (3 if mode == "peer" else 0)
     torch.cuda.synchronize()
@@ -749,7 +844,10 @@ def main():
             "l2": L2_NOTE, "parallelism": par,
             "call": ("mhb_spgemm_into_f64: caller-owned C arrays kept across steps, one host synchronisation per SpGEMM"
                      if fused else "mhb_symbolic + mhb_numeric_f64: two calls, host reads nnz(C) in between"),
-            "fused_calls": stats.get("fused_calls"), "speculative_misses": stats.get("speculative_misses"), "exchange_bytes_received_rank0": exch_bytes, "slices_rank0": len(slices),
+            "fused_calls": stats.get("fused_calls"), "speculative_misses": stats.get("speculative_misses"),
+            "timed_region": ("start event | exchange, every kernel of the SpGEMM, slice-size post | stop event, all queued "
+                             "before the host waits (mhb_spgemm_into_begin / _end)" if device_bracket else
+                             "start event | the whole step including its host synchronisations | stop event"), "exchange_bytes_received_rank0": exch_bytes, "slices_rank0": len(slices),
             "roofline": {"bound": "hbm",
                          "kernel": "numeric: " + " + ".join(kernels) + ("" if len(kernels) == 1 else " (bins run concurrently)"),
                          "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -775,6 +873,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(A, B, intprod)
+        if world == 1 and args.workload == "F" and not args.no_perturbed:
+            line["perturbed_fem"] = perturbed_fem(tool, torch, dev)
         if world == 1 and args.workload == "F" and not args.no_suite:
             line["suite"] = suite_breadth(tool)
         print(json.dumps(line), file=real_stdout, flush=True)

@@ -133,6 +133,20 @@ int mhb_spgemm_into_f32(mhb_handle_t h, int M, int K, int N,
                         int nnzA, const int *dA_ptr, const int *dA_col, const float *dA_val,
                         int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
                         int *dC_ptr, int *dC_col, float *dC_val, long long capacity, long long *nnzC);
+/* The same call in two halves, for callers that overlap host work with the SpGEMM or time it with
+ * their own events: begin queues the work on the handle's stream and returns without waiting (in
+ * steady state; the first call of a shape runs its symbolic phase to completion inside begin),
+ * end synchronises, verifies, re-runs on a miss and reports nnz(C) / MHB_ERR_CAPACITY.  One
+ * outstanding begin per handle; the arrays must stay valid until end returns. */
+int mhb_spgemm_into_begin_f64(mhb_handle_t h, int M, int K, int N,
+                              int nnzA, const int *dA_ptr, const int *dA_col, const double *dA_val,
+                              int nnzB, const int *dB_ptr, const int *dB_col, const double *dB_val,
+                              int *dC_ptr, int *dC_col, double *dC_val, long long capacity);
+int mhb_spgemm_into_begin_f32(mhb_handle_t h, int M, int K, int N,
+                              int nnzA, const int *dA_ptr, const int *dA_col, const float *dA_val,
+                              int nnzB, const int *dB_ptr, const int *dB_col, const float *dB_val,
+                              int *dC_ptr, int *dC_col, float *dC_val, long long capacity);
+int mhb_spgemm_into_end(mhb_handle_t h, long long *nnzC);
 int mhb_device_free(void *dptr);
 /* Raw device buffers and copies for callers without their own CUDA runtime binding: the
  * pieces of CSR::H2D / CSR::D2H (src/CSR.cu:97-120).  Synchronous. */
@@ -189,6 +203,10 @@ int mhb_get_bins(mhb_handle_t h, int which, int *nbins, const int **d_bins,
 /* cudaStream_t the handle currently launches on (for callers that order their own work). */
 int mhb_get_stream(mhb_handle_t h, void **cuda_stream);
 
+/* Device-side results of the call last queued on the handle, readable in stream order by the
+ * caller's own kernels without a host round trip: nnz(C), and the gate word of a fused call
+ * (non-zero: the numeric phase stood down and mhb_spgemm_into_end will redo or report). */
+int mhb_get_device_scalars(mhb_handle_t h, const long long **d_nnzC, const int **d_gate);
 int mhb_get_timing(mhb_handle_t h, mhb_timing *out);
 int mhb_get_stats(mhb_handle_t h, mhb_stats *out);
 
@@ -263,9 +281,21 @@ int mhb_shard_spgemm_into_f64(mhb_shard_t s, int r_lo, int r_hi, const double *d
                               double *dC_val, long long capacity, long long *nnzC);
 int mhb_shard_spgemm_into_f32(mhb_shard_t s, int r_lo, int r_hi, const float *dA_val, int *dC_ptr, int *dC_col,
                               float *dC_val, long long capacity, long long *nnzC);
+/* ... and in two halves (mhb_spgemm_into_begin_* / mhb_spgemm_into_end). */
+int mhb_shard_spgemm_into_begin_f64(mhb_shard_t s, int r_lo, int r_hi, const double *dA_val, int *dC_ptr, int *dC_col,
+                                    double *dC_val, long long capacity);
+int mhb_shard_spgemm_into_begin_f32(mhb_shard_t s, int r_lo, int r_hi, const float *dA_val, int *dC_ptr, int *dC_col,
+                                    float *dC_val, long long capacity);
+int mhb_shard_spgemm_into_end(mhb_shard_t s, long long *nnzC);
 /* Publish this rank's nnz(C slice) of the step to every rank (one-sided, stream-ordered);
  * mhb_shard_offsets waits for all of them: offset of this rank's slice and the total. */
 int mhb_shard_post_size(mhb_shard_t s, long long nnzC_local);
+/* nnzC_local = -1 posts the device-side nnz(C) of the SpGEMM just queued with
+ * mhb_shard_spgemm_into_begin_* (no host read in between).  If that call turns out to need a redo
+ * (speculation miss) the posted value is a "pending" marker that mhb_shard_offsets waits on;
+ * mhb_shard_repost_size(s, nnz) after mhb_shard_spgemm_into_end then supplies the value for the
+ * SAME step (idempotent when nothing was pending). */
+int mhb_shard_repost_size(mhb_shard_t s, long long nnzC_local);
 int mhb_shard_offsets(mhb_shard_t s, long long *slice_offset, long long *nnzC_total,
                       long long *all_sizes /* world entries, may be NULL */);
 

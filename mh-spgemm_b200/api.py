@@ -26,14 +26,17 @@ LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
 SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
-            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT", "H_BLOCK_M", "H_BLOCK_XS",
-            "TINY_S", "TINY_M"]
+            "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT",
+            "H_BLOCK_M", "H_BLOCK_XS"]
 
 # every symbol include/mhb_spgemm.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "mhb_version", "mhb_create", "mhb_destroy", "mhb_last_error", "mhb_set_stream", "mhb_set_option",
     "mhb_symbolic", "mhb_numeric_f64", "mhb_numeric_f32", "mhb_spgemm_f64", "mhb_spgemm_f32",
     "mhb_spgemm_into_f64", "mhb_spgemm_into_f32", "mhb_shard_spgemm_into_f64", "mhb_shard_spgemm_into_f32",
+    "mhb_spgemm_into_begin_f64", "mhb_spgemm_into_begin_f32", "mhb_spgemm_into_end",
+    "mhb_shard_spgemm_into_begin_f64", "mhb_shard_spgemm_into_begin_f32", "mhb_shard_spgemm_into_end",
+    "mhb_shard_repost_size", "mhb_get_device_scalars",
     "mhb_device_free", "mhb_device_alloc", "mhb_memcpy_h2d", "mhb_memcpy_d2h", "mhb_spgemm_host_f64", "mhb_spgemm_host_f32", "mhb_host_alloc", "mhb_host_free",
     "mhb_form_mask_matrix_B", "mhb_get_row_info", "mhb_get_bins", "mhb_get_timing", "mhb_get_stats",
     "mhb_transpose_f64", "mhb_transpose_f32", "mhb_get_stream",
@@ -103,6 +106,12 @@ def load_library() -> C.CDLL:
         getattr(L, n).argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, ll, C.POINTER(ll)]
     for n in ("mhb_shard_spgemm_into_f64", "mhb_shard_spgemm_into_f32"):
         getattr(L, n).argtypes = [vp, ip, ip, vp, vp, vp, vp, ll, C.POINTER(ll)]
+    for n in ("mhb_spgemm_into_begin_f64", "mhb_spgemm_into_begin_f32"):
+        getattr(L, n).argtypes = [vp, ip, ip, ip, ip, vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, ll]
+    for n in ("mhb_shard_spgemm_into_begin_f64", "mhb_shard_spgemm_into_begin_f32"):
+        getattr(L, n).argtypes = [vp, ip, ip, vp, vp, vp, vp, ll]
+    L.mhb_spgemm_into_end.argtypes = [vp, C.POINTER(ll)]
+    L.mhb_shard_spgemm_into_end.argtypes = [vp, C.POINTER(ll)]
     L.mhb_device_free.argtypes = [vp]
     L.mhb_device_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.mhb_memcpy_h2d.argtypes = [vp, vp, C.c_size_t]
@@ -130,6 +139,8 @@ def load_library() -> C.CDLL:
     L.mhb_shard_numeric_f64.argtypes = [vp, vp, vp, vp]
     L.mhb_shard_numeric_f32.argtypes = [vp, vp, vp, vp]
     L.mhb_shard_post_size.argtypes = [vp, ll]
+    L.mhb_shard_repost_size.argtypes = [vp, ll]
+    L.mhb_get_device_scalars.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mhb_shard_offsets.argtypes = [vp, C.POINTER(ll), C.POINTER(ll), C.POINTER(ll)]
     L.mhb_nccl_unique_id.argtypes = [vp]
     L.mhb_shard_init_nccl.argtypes = [vp, vp]
@@ -327,6 +338,27 @@ class Tool:
         rc = f(self.h, M, K, N, dA_col.numel(), dA_ptr.data_ptr(), dA_col.data_ptr(), dA_val.data_ptr(),
                dB_col.numel(), dB_ptr.data_ptr(), dB_col.data_ptr(), dB_val.data_ptr(), dC_ptr.data_ptr(),
                dC_col.data_ptr() if cap else None, dC_val.data_ptr() if cap else None, cap, C.byref(nnz))
+        if rc == ERR_CAPACITY:
+            e = MhbError(rc, self.L.mhb_last_error(self.h).decode())
+            e.nnzC = int(nnz.value)
+            raise e
+        self._chk(rc)
+        return int(nnz.value)
+
+    def spgemm_into_begin(self, M, K, N, dA_ptr, dA_col, dA_val, dB_ptr, dB_col, dB_val, dC_ptr, dC_col, dC_val):
+        """First half of spgemm_into: queues the SpGEMM on the handle's stream and returns without
+        waiting (steady state).  Follow with spgemm_into_end()."""
+        f = self.L.mhb_spgemm_into_begin_f64 if _itemsize(dA_val) == 8 else self.L.mhb_spgemm_into_begin_f32
+        self._keep = (dA_ptr, dA_col, dA_val, dB_ptr, dB_col, dB_val, dC_ptr, dC_col, dC_val)
+        cap = min(dC_col.numel(), dC_val.numel()) if dC_col is not None else 0
+        self._chk(f(self.h, M, K, N, dA_col.numel(), dA_ptr.data_ptr(), dA_col.data_ptr(), dA_val.data_ptr(),
+                    dB_col.numel(), dB_ptr.data_ptr(), dB_col.data_ptr(), dB_val.data_ptr(), dC_ptr.data_ptr(),
+                    dC_col.data_ptr() if cap else None, dC_val.data_ptr() if cap else None, cap))
+
+    def spgemm_into_end(self) -> int:
+        """Second half: synchronises, verifies; returns nnz(C) or raises (ERR_CAPACITY carries .nnzC)."""
+        nnz = C.c_longlong()
+        rc = self.L.mhb_spgemm_into_end(self.h, C.byref(nnz))
         if rc == ERR_CAPACITY:
             e = MhbError(rc, self.L.mhb_last_error(self.h).decode())
             e.nnzC = int(nnz.value)

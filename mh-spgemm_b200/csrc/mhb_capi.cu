@@ -107,6 +107,21 @@ enum Ev
 
 } // namespace
 
+namespace
+{
+// a mhb_spgemm_into_begin_* whose mhb_spgemm_into_end is outstanding
+struct IntoCall
+{
+    bool active = false, pending = false, over = false;
+    int M = 0, K = 0, N = 0, nnzA = 0, nnzB = 0, vbytes = 0;
+    const int *Ap = nullptr, *Ac = nullptr, *Bp = nullptr, *Bc = nullptr;
+    const void *Av = nullptr, *Bv = nullptr;
+    int *Cp = nullptr, *Cc = nullptr;
+    void *Cv = nullptr;
+    long long capacity = 0, nnzC = 0;
+};
+} // namespace
+
 struct mhb_context
 {
     int device = 0;
@@ -136,6 +151,7 @@ struct mhb_context
     int fused_launched[MHB_MAX_BINS + 1] = {0};
     int fused_planned_tileflop = 0;
     int fused_calls = 0;
+    IntoCall into;
     int mask_onepass = 1;                // option "mask_onepass": one-pass mask builder (0: the round-1 five-kernel chain)
     int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
@@ -217,14 +233,11 @@ int fail(mhb_context *h, int code, const std::string &msg)
 
 // Fork / join of the per-bin kernels of one phase: bin kernels are independent (disjoint rows,
 // disjoint outputs), so they are spread over the main stream and kAux helper streams.
-int fork_bins(mhb_context *h, const int *off, int nbins)
+int fork_bins(mhb_context *h, int populated /* kernels of the phase */)
 {
     h->aux_used = 0;
-    // a phase with a single populated bin (FEM-like inputs) stays on the main stream: no
-    // event round trip to a helper stream and back
-    int populated = 0;
-    for (int b = 1; b < nbins; ++b) // bin 0 is the empty-row bin: no kernel
-        populated += off[b + 1] > off[b];
+    // a phase with a single kernel (FEM-like inputs) stays on the main stream: no event round
+    // trip to a helper stream and back
     h->phase_serial = h->serial || populated <= 1;
     if (h->phase_serial)
         return MHB_OK;
@@ -432,6 +445,26 @@ int check_dev_error(mhb_context *h, const int *hs)
     return MHB_OK;
 }
 
+// Bins that get a kernel when a phase is launched from the offsets `off`: the populated ones; the
+// three cost classes of the thread-per-row kernel (adjacent bins t0 .. t0+2) share ONE launch, so
+// all of them are covered as soon as one is populated.
+unsigned launched_mask(const int *off, int nbins, int t0)
+{
+    unsigned m = 0;
+    for (int b = 1; b < nbins; ++b) // bin 0 (rows without products) has no kernel
+        m |= (off[b + 1] > off[b]) ? (1u << b) : 0u;
+    const unsigned tiny = 7u << t0;
+    if (m & tiny)
+        m |= tiny;
+    return m;
+}
+// kernels behind a launched mask (the tiny family counts once)
+int launched_kernels(unsigned m, int t0)
+{
+    const unsigned tiny = 7u << t0;
+    return __builtin_popcount(m & ~tiny) + ((m & tiny) ? 1 : 0);
+}
+
 // ---- family 3 launches ------------------------------------------------------------------
 // spec: the host has NOT read this call's bin sizes; h->sym_off / h->max_tileflop are those of the
 // previous call on the handle and only size the grids and scratch -- the kernels take their
@@ -461,7 +494,7 @@ int launch_symbolic_bins(mhb_context *h, bool spec)
         a_twins = (h->Ap == h->Bp && h->Ac == h->Bc) ? h->bsame.as<unsigned char>()
                                                      : (h->asame_early ? h->asame_buf.as<unsigned char>() : nullptr);
     h->have_bm_store = false;
-    int frc = fork_bins(h, off, SB_COUNT);
+    int frc = fork_bins(h, launched_kernels(launched_mask(off, SB_COUNT, SB_TINY), SB_TINY));
     if (frc)
         return frc;
     // big-row bins first (see launch_numeric_bins)
@@ -539,13 +572,16 @@ int launch_symbolic_bins(mhb_context *h, bool spec)
                SB_BM_G8_WORDS, h->bsame.as<unsigned char>(), h->have_bm_store ? h->bm_store.as<unsigned>() : nullptr,
                h->have_bm_store ? h->bm_slot.as<int>() : nullptr, a_twins, n, scal);
     }
-    for (int tb : {(int)SB_TINY, (int)SB_TINY_M, (int)SB_TINY_S}) // the same kernel per cost class
-        if ((n = n_of(tb)) > 0)
-        {
-            if (int e_ = next_bin_stream(h, &st)) return e_;
-            LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, list(tb),
-                      h->Ap, h->Ac, tp, tc, tm, counts);
-        }
+    // the three cost classes of the thread-per-row kernel: adjacent bins, one launch over rows sorted by class
+    static_assert(SB_TINY_S == SB_TINY + 1 && SB_TINY_M == SB_TINY + 2, "tiny classes must be adjacent bins");
+    if ((n = off[SB_TINY + 3] - off[SB_TINY]) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        RowList tl = spec ? RowList{bins, scal + SC_SYM_OFF + SB_TINY, -1, nullptr, 3}
+                          : RowList{bins + off[SB_TINY], nullptr, n, nullptr, 1};
+        LAUNCH_ON(h, st, k_sym_tiny, std::min(cdiv(n, kTinyThreads), cap_blocks), kTinyThreads, 0, tl,
+                  h->Ap, h->Ac, tp, tc, tm, counts);
+    }
     return join_bins(h);
 }
 
@@ -577,7 +613,7 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     const int *Ap = h->Ap, *Ac = h->Ac, *Bp = h->Bp, *Bc = h->Bc, *Cp = h->Cp;
     int n;
     cudaStream_t st;
-    int frc = fork_bins(h, off, NB_COUNT);
+    int frc = fork_bins(h, launched_kernels(launched_mask(off, NB_COUNT, NB_TINY), NB_TINY));
     if (frc)
         return frc;
     // k_num_hash_list over one bin.  threads = 0: four rows (warps) per 128-thread block, each warp
@@ -780,14 +816,16 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
                GPB * NB_H_G8_SLOTS * (sizeof(T) + 4), list(NB_H_G8), Ap, Ac, Av, Bp, Bc, Bv, arow, Cp, Cc, Cv,
                log2_ceil(NB_H_G8_SLOTS), scal, probes);
     }
-    for (int tb : {(int)NB_TINY, (int)NB_TINY_M, (int)NB_TINY_S}) // the same kernel per cost class
-        if ((n = n_of(tb)) > 0)
-        {
-            if (int e_ = next_bin_stream(h, &st)) return e_;
-            LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
-                      NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4),
-                      list(tb), Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
-        }
+    // the three cost classes of the thread-per-row kernel: adjacent bins, one launch over rows sorted by class
+    static_assert(NB_TINY_S == NB_TINY + 1 && NB_TINY_M == NB_TINY + 2, "tiny classes must be adjacent bins");
+    if ((n = off[NB_TINY + 3] - off[NB_TINY]) > 0)
+    {
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        RowList tl = spec ? RowList{bins, scal + SC_NUM_OFF + NB_TINY, -1, scal + SC_GATE, 3}
+                          : RowList{bins + off[NB_TINY], nullptr, n, nullptr, 1};
+        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
+                  NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4), tl, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+    }
     return join_bins(h);
 }
 
@@ -950,11 +988,8 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
         // fused call: no host read here.  The verdict on this call's speculation is formed on the
         // device (k_fused_gate) and the caller launches the numeric kernels behind it; the host reads
         // the scalars once, after the numeric phase (finish_symbolic).
-        unsigned sym_mask = 0, num_mask = 0;
-        for (int b = 1; b < SB_COUNT; ++b)
-            sym_mask |= (launched[b + 1] > launched[b]) ? (1u << b) : 0u;
-        for (int b = 1; b < NB_COUNT; ++b)
-            num_mask |= (h->num_off[b + 1] > h->num_off[b]) ? (1u << b) : 0u;
+        const unsigned sym_mask = launched_mask(launched, SB_COUNT, SB_TINY);
+        const unsigned num_mask = launched_mask(h->num_off, NB_COUNT, NB_TINY);
         LAUNCH(h, k_fused_gate, 1, 32, 0, scal, sym_mask, planned_tileflop, num_mask, h->max_rownnz,
                std::min<long long>(fused_capacity, h->nnz_limit), (int)SB_H_GLOBAL, (int)NB_H_GLOBAL, (int)SB_COUNT,
                (int)NB_COUNT);
@@ -973,8 +1008,9 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     if (spec)
     {
         bool miss = hs[SC_SPEC_MISS] != 0;
+        const unsigned sym_mask = launched_mask(launched, SB_COUNT, SB_TINY);
         for (int b = 1; b < SB_COUNT; ++b) // bin 0 (rows without products) has no kernel
-            miss |= hs[SC_SYM_SIZE + b] > 0 && launched[b + 1] == launched[b];
+            miss |= hs[SC_SYM_SIZE + b] > 0 && !((sym_mask >> b) & 1u);
         // the global tile-hash pool was sized from the previous call's largest row (checked per row in the kernel too)
         miss |= hs[SC_SYM_SIZE + SB_H_GLOBAL] > 0 && hs[SC_MAX_TILEFLOP] > planned_tileflop;
         if (miss)
@@ -1087,6 +1123,121 @@ int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sy
     return MHB_OK;
 }
 
+// begin: validates, launches (in steady state: everything, without a host read), returns without
+// waiting.  end: the one synchronisation, the verdict of the gate, the redo on a miss.
+template <typename T>
+int into_begin(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, const int *Ac, const T *Av, int nnzB,
+               const int *Bp, const int *Bc, const T *Bv, int *Cp, int *Cc, T *Cv, long long capacity)
+{
+    IntoCall &ic = h->into;
+    ic = IntoCall{};
+    if (capacity < 0 || (capacity > 0 && (!Cc || !Cv)))
+        return fail(h, MHB_ERR_ARG, "null output pointer / negative capacity");
+    if ((nnzA > 0 && !Av) || (nnzB > 0 && !Bv))
+        return fail(h, MHB_ERR_ARG, "null value pointer");
+    ic.M = M, ic.K = K, ic.N = N, ic.nnzA = nnzA, ic.nnzB = nnzB;
+    ic.Ap = Ap, ic.Ac = Ac, ic.Av = Av, ic.Bp = Bp, ic.Bc = Bc, ic.Bv = Bv, ic.Cp = Cp, ic.Cc = Cc, ic.Cv = Cv;
+    ic.capacity = capacity, ic.vbytes = (int)sizeof(T);
+    int rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, &ic.nnzC, true, capacity);
+    if (rc)
+        return rc;
+    ic.active = true;
+    if (h->fused_pending)
+    {
+        h->fused_pending = false;
+        ++h->fused_calls;
+        ic.pending = true;
+        rc = prepare_a_twins(h);
+        if (rc)
+            return rc;
+        CU(cudaEventRecord(h->ev[EV_NUM0], h->stream));
+        rc = launch_numeric_bins<T>(h, Av, Bv, Cc, Cv, true);
+        if (rc)
+            return rc;
+        CU(cudaEventRecord(h->ev[EV_NUM1], h->stream));
+        CU(cudaMemcpyAsync(h->h_scal.as<int>(), h->scal.as<int>(), SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
+        return MHB_OK;
+    }
+    // ordinary path (first call of a shape): the symbolic phase has synchronised and nnz(C) is known
+    if (ic.nnzC > capacity)
+    {
+        ic.over = true; // reported by end
+        return MHB_OK;
+    }
+    return do_numeric<T>(h, Av, Bv, Cc, Cv, false);
+}
+
+int numeric_finish(mhb_context *h)
+{
+    int *hs = h->h_scal.as<int>();
+    CU(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int rc = check_dev_error(h, hs);
+    if (rc)
+        return rc;
+    std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
+    h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
+    if (h->ev_sym_valid)
+        h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
+    return MHB_OK;
+}
+
+int capacity_error(mhb_context *h, long long nnz, long long capacity)
+{
+    return fail(h, MHB_ERR_CAPACITY, "nnz(C) = " + std::to_string(nnz) + " exceeds the capacity of the caller's C arrays (" +
+                                         std::to_string(capacity) + "); row_ptr is valid, grow C.col / C.val and call again");
+}
+
+template <typename T>
+int into_end(mhb_context *h, long long *nnzC)
+{
+    IntoCall ic = h->into;
+    h->into.active = false;
+    if (!nnzC)
+        return fail(h, MHB_ERR_ARG, "null nnzC");
+    *nnzC = 0;
+    if (!ic.active || ic.vbytes != (int)sizeof(T))
+        return fail(h, MHB_ERR_ARG, "mhb_spgemm_into_end without a matching mhb_spgemm_into_begin_*");
+    const T *Av = static_cast<const T *>(ic.Av), *Bv = static_cast<const T *>(ic.Bv);
+    T *Cv = static_cast<T *>(ic.Cv);
+    if (!ic.pending)
+    {
+        *nnzC = ic.nnzC;
+        if (ic.over)
+            return capacity_error(h, ic.nnzC, ic.capacity);
+        return numeric_finish(h);
+    }
+    int *hs = h->h_scal.as<int>();
+    CU(cudaStreamSynchronize(h->stream)); // the one host read of the call
+    const int gate = hs[SC_GATE];
+    // SC_SPEC_MISS raised after the gate: a pool row of the numeric phase outgrew the planned table
+    const bool late_miss = gate == 0 && hs[SC_SPEC_MISS] != 0;
+    if ((gate & (GATE_SYM_MISS | GATE_NUM_MISS)) || late_miss)
+    {
+        ++h->spec_misses; // redo the ordinary way
+        int rc = do_symbolic(h, ic.M, ic.K, ic.N, ic.nnzA, ic.Ap, ic.Ac, ic.nnzB, ic.Bp, ic.Bc, ic.Cp, nnzC, false);
+        if (rc)
+            return rc;
+        if (*nnzC > ic.capacity)
+            return capacity_error(h, *nnzC, ic.capacity);
+        return do_numeric<T>(h, Av, Bv, ic.Cc, Cv, true);
+    }
+    int rc = check_dev_error(h, hs);
+    if (rc)
+        return rc;
+    rc = finish_symbolic(h, hs, nnzC);
+    if (rc)
+        return rc;
+    if (gate & GATE_CAPACITY)
+        return capacity_error(h, h->nnzC, ic.capacity);
+    h->have_pattern = true; // (A's twin flags were formed in begin, for the same set of bins)
+    h->stats.gpu_launches = h->launches;
+    std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
+    h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
+    h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
+    return MHB_OK;
+}
+
 // The fused call: C = A*B into caller-owned C arrays of `capacity` entries.  A caller that
 // multiplies the same shapes repeatedly (the loop of src/main.cu:118-125, an AMG setup, a
 // time-stepping code) keeps its C buffers, so the hand-off of src/main.cu:55-60 -- read nnz(C),
@@ -1101,62 +1252,16 @@ int do_spgemm_into(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap,
                    const int *Bp, const int *Bc, const T *Bv, int *Cp, int *Cc, T *Cv, long long capacity,
                    long long *nnzC)
 {
-    if (!nnzC || capacity < 0 || (capacity > 0 && (!Cc || !Cv)))
-        return fail(h, MHB_ERR_ARG, "null output pointer / negative capacity");
-    if ((nnzA > 0 && !Av) || (nnzB > 0 && !Bv))
-        return fail(h, MHB_ERR_ARG, "null value pointer");
+    if (!nnzC)
+        return fail(h, MHB_ERR_ARG, "null nnzC");
     *nnzC = 0;
-    int rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC, true, capacity);
+    int rc = into_begin<T>(h, M, K, N, nnzA, Ap, Ac, Av, nnzB, Bp, Bc, Bv, Cp, Cc, Cv, capacity);
     if (rc)
-        return rc;
-    if (h->fused_pending)
     {
-        h->fused_pending = false;
-        ++h->fused_calls;
-        int *hs = h->h_scal.as<int>();
-        rc = prepare_a_twins(h);
-        if (rc)
-            return rc;
-        CU(cudaEventRecord(h->ev[EV_NUM0], h->stream));
-        rc = launch_numeric_bins<T>(h, Av, Bv, Cc, Cv, true);
-        if (rc)
-            return rc;
-        CU(cudaEventRecord(h->ev[EV_NUM1], h->stream));
-        CU(cudaMemcpyAsync(hs, h->scal.as<int>(), SC_COUNT * 4, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream)); // the one host read of the call
-        const int gate = hs[SC_GATE];
-        // SC_SPEC_MISS raised after the gate: a pool row of the numeric phase outgrew the planned table
-        const bool late_miss = gate == 0 && hs[SC_SPEC_MISS] != 0;
-        if ((gate & (GATE_SYM_MISS | GATE_NUM_MISS)) || late_miss)
-        {
-            ++h->spec_misses; // redo the ordinary way (below)
-            rc = do_symbolic(h, M, K, N, nnzA, Ap, Ac, nnzB, Bp, Bc, Cp, nnzC, false);
-            if (rc)
-                return rc;
-        }
-        else
-        {
-            rc = check_dev_error(h, hs);
-            if (rc)
-                return rc;
-            rc = finish_symbolic(h, hs, nnzC);
-            if (rc)
-                return rc;
-            if (gate & GATE_CAPACITY)
-                return fail(h, MHB_ERR_CAPACITY, "nnz(C) = " + std::to_string(h->nnzC) + " exceeds the capacity of the caller's C arrays (" +
-                                                     std::to_string(capacity) + "); row_ptr is valid, grow C.col / C.val and call again");
-            h->have_pattern = true;
-            h->stats.gpu_launches = h->launches;
-            std::memcpy(&h->stats.hash_probes, hs + SC_PROBES_LO, 8);
-            h->timing.numeric = ev_ms(h, EV_NUM0, EV_NUM1);
-            h->timing.total = ev_ms(h, EV_START, EV_HANDOFF) + h->timing.numeric;
-            return MHB_OK;
-        }
+        h->into.active = false;
+        return rc;
     }
-    if (*nnzC > capacity)
-        return fail(h, MHB_ERR_CAPACITY, "nnz(C) = " + std::to_string(*nnzC) + " exceeds the capacity of the caller's C arrays (" +
-                                             std::to_string(capacity) + "); row_ptr is valid, grow C.col / C.val and call again");
-    return do_numeric<T>(h, Av, Bv, Cc, Cv, true);
+    return into_end<T>(h, nnzC);
 }
 
 template <typename T>
@@ -1551,6 +1656,30 @@ extern "C"
         return do_spgemm_into<float>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr,
                                      dC_col, dC_val, capacity, nnzC);
     }
+    int mhb_spgemm_into_begin_f64(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                                  const double *dA_val, int nnzB, const int *dB_ptr, const int *dB_col,
+                                  const double *dB_val, int *dC_ptr, int *dC_col, double *dC_val, long long capacity)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return into_begin<double>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr, dC_col,
+                                  dC_val, capacity);
+    }
+    int mhb_spgemm_into_begin_f32(mhb_handle_t h, int M, int K, int N, int nnzA, const int *dA_ptr, const int *dA_col,
+                                  const float *dA_val, int nnzB, const int *dB_ptr, const int *dB_col,
+                                  const float *dB_val, int *dC_ptr, int *dC_col, float *dC_val, long long capacity)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return into_begin<float>(h, M, K, N, nnzA, dA_ptr, dA_col, dA_val, nnzB, dB_ptr, dB_col, dB_val, dC_ptr, dC_col,
+                                 dC_val, capacity);
+    }
+    int mhb_spgemm_into_end(mhb_handle_t h, long long *nnzC)
+    {
+        if (!h)
+            return MHB_ERR_ARG;
+        return h->into.vbytes == 4 ? into_end<float>(h, nnzC) : into_end<double>(h, nnzC);
+    }
     int mhb_device_free(void *dptr) { return cudaFree(dptr) == cudaSuccess ? MHB_OK : MHB_ERR_CUDA; }
     int mhb_device_alloc(void **dptr, size_t bytes)
     {
@@ -1660,6 +1789,17 @@ extern "C"
         *nbins = which == 0 ? (int)SB_COUNT : (int)NB_COUNT;
         *d_bins = which == 0 ? h->bins_sym.as<int>() : h->bins_num.as<int>();
         std::memcpy(h_bin_offset, which == 0 ? h->sym_off : h->num_off, sizeof(int) * (MHB_MAX_BINS + 1));
+        return MHB_OK;
+    }
+
+    int mhb_get_device_scalars(mhb_handle_t h, const long long **d_nnzC, const int **d_gate)
+    {
+        if (!h || !d_nnzC || !d_gate)
+            return MHB_ERR_ARG;
+        if (!h->scal.p)
+            return fail(h, MHB_ERR_ARG, "no call on this handle yet");
+        *d_nnzC = reinterpret_cast<const long long *>(h->scal.as<int>() + SC_NNZC_LO);
+        *d_gate = h->scal.as<int>() + SC_GATE;
         return MHB_OK;
     }
 

@@ -117,12 +117,13 @@ struct RowList
     const int *off;
     int n;
     const int *gate; // optional (fused call): when *gate != 0 the list reads as empty and the kernel stands down
+    int span = 1;    // adjacent bins the list covers (the three cost classes of the thread-per-row kernels)
     __device__ __forceinline__ const int *begin() const { return n >= 0 ? rows : rows + off[0]; }
     __device__ __forceinline__ int size() const
     {
         if (gate && *gate)
             return 0;
-        return n >= 0 ? n : off[1] - off[0];
+        return n >= 0 ? n : off[span] - off[0];
     }
 };
 

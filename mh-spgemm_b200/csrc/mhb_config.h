@@ -29,9 +29,11 @@ enum MhbSymBin
     SB_H_BLOCK_L,   // tile hash, block/row,   ub <= 12288 (16384 slots)
     SB_H_GLOBAL,    // tile hash in global memory
     SB_TINY,        // one thread per row, tile list in shared memory, tile-flop <= 24
-    SB_TINY_S,      // the same kernel on the rows with tile-flop <= 4 ...
-    SB_TINY_M,      // ... and <= 12: threads of one warp then carry rows of similar cost (on power-law
-                    // inputs the rows of one bin differ 100x and a warp ran 4 of its 32 lanes, r2l)
+    SB_TINY_S,      // the same kernel, rows with tile-flop <= 4 ...
+    SB_TINY_M,      // ... and <= 12.  The three classes are adjacent in the bin list and run as ONE launch
+                    // over rows sorted by class: the threads of a warp then carry rows of similar cost (on
+                    // power-law inputs the rows of the old single bin differed 100x in cost and a warp ran
+                    // 4 of its 32 lanes, profiles/r2l_hash_kernels_R.md)
     SB_COUNT
 };
 #define SB_BM_G8_WORDS 64
@@ -65,14 +67,15 @@ enum MhbNumBin
     NB_H_BLOCK_L,   // hash, block/row,   n <= 10240 (16384 slots)
     NB_H_GLOBAL,    // hash in global memory
     NB_TINY,        // one thread per row, n <= 24 and <= 128 products
+    NB_TINY_S,      // NB_TINY's kernel, rows with <= 8 products ...
+    NB_TINY_M,      // ... and <= 32 products: the three classes are adjacent in the bin list and run as ONE
+                    // launch over rows sorted by class (see SB_TINY_S)
     NB_H_WARP_XS,   // hash, warp/row,    n <= 80  (128 slots)
     NB_H_WARP_M,    // hash, warp/row,    n <= 320 (512 slots)
     NB_WIN_COMPACT, // window rows with a stored symbolic bitmap, n <= 448: rank-mapped accumulators,
                     // up to three twin rows of A per warp
     NB_H_BLOCK_M,   // hash, block/row,   n <= 5120 (8192 slots, claim list)
     NB_H_BLOCK_XS,  // hash, block/row,   n <= 1280 (2048 slots, claim list, 128 threads)
-    NB_TINY_S,      // NB_TINY's kernel on the rows with <= 8 products ...
-    NB_TINY_M,      // ... and <= 32 products (see SB_TINY_S)
     NB_COUNT
 };
 #define NB_WIN_G8_COLS 256

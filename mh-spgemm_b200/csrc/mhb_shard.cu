@@ -162,6 +162,24 @@ __global__ void k_shard_post(PeerMail pm, int world, int rank, unsigned long lon
     }
 }
 
+// The same post with the value taken from the device: nnz(C) of the SpGEMM the handle has just
+// queued (mhb_spgemm_into_begin_*), without the host having seen it.  When the call's speculation
+// gate says the numeric phase stood down (the host will redo it in mhb_spgemm_into_end), the value
+// is not final: kSizePending is posted instead and mhb_shard_repost_size follows the redo.
+constexpr unsigned long long kSizePending = ~0ull;
+__global__ void k_shard_post_dev(PeerMail pm, int world, int rank, const long long *__restrict__ d_nnz,
+                                 const int *__restrict__ d_gate, unsigned long long epoch)
+{
+    const int p = threadIdx.x;
+    if (p < world)
+    {
+        const unsigned long long value = (*d_gate != 0) ? kSizePending : (unsigned long long)*d_nnz;
+        st_sys(pm.mail[p] + MAIL_SIZE_VAL * world + rank, value);
+        __threadfence_system();
+        st_sys(pm.mail[p] + MAIL_SIZE_EP * world + rank, epoch);
+    }
+}
+
 __global__ void k_shard_wait_sizes(const unsigned long long *mail, int world, unsigned long long epoch,
                                    unsigned long long *out, int *err)
 {
@@ -171,7 +189,19 @@ __global__ void k_shard_wait_sizes(const unsigned long long *mail, int world, un
         if (!wait_ge(mail + MAIL_SIZE_EP * world + o, epoch))
             atomicExch(err, 1);
         __threadfence_system();
-        out[o] = ld_sys(mail + MAIL_SIZE_VAL * world + o);
+        unsigned long long v = ld_sys(mail + MAIL_SIZE_VAL * world + o);
+        const unsigned long long t0 = now_ns();
+        while (v == kSizePending) // the owner is redoing its SpGEMM and will repost
+        {
+            if (now_ns() - t0 > kWaitNs)
+            {
+                atomicExch(err, 1);
+                break;
+            }
+            __nanosleep(200);
+            v = ld_sys(mail + MAIL_SIZE_VAL * world + o);
+        }
+        out[o] = v;
     }
 }
 
@@ -740,11 +770,65 @@ extern "C"
         return rc;
     }
 
+    int mhb_shard_spgemm_into_begin_f64(mhb_shard_t s, int r_lo, int r_hi, const double *dA_val, int *dC_ptr,
+                                        int *dC_col, double *dC_val, long long capacity)
+    {
+        if (!s || s->phase != 3 || s->vbytes != 8 || r_lo < 0 || r_hi < r_lo || r_hi > s->M)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_spgemm_into_begin_f64: bad row range, incomplete plan or value type mismatch");
+        int rc = mhb_spgemm_into_begin_f64(s->h, r_hi - r_lo, s->i1 - s->i0, s->N, s->nnzA, s->Ap + r_lo, s->Ac_local,
+                                           dA_val, (int)s->nnz_img, s->img_ptr, reinterpret_cast<const int *>(s->w2),
+                                           reinterpret_cast<const double *>(s->w2 + s->val_byte_off), dC_ptr, dC_col,
+                                           dC_val, capacity);
+        if (rc)
+            s->err = mhb_last_error(s->h);
+        return rc;
+    }
+    int mhb_shard_spgemm_into_begin_f32(mhb_shard_t s, int r_lo, int r_hi, const float *dA_val, int *dC_ptr,
+                                        int *dC_col, float *dC_val, long long capacity)
+    {
+        if (!s || s->phase != 3 || s->vbytes != 4 || r_lo < 0 || r_hi < r_lo || r_hi > s->M)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_spgemm_into_begin_f32: bad row range, incomplete plan or value type mismatch");
+        int rc = mhb_spgemm_into_begin_f32(s->h, r_hi - r_lo, s->i1 - s->i0, s->N, s->nnzA, s->Ap + r_lo, s->Ac_local,
+                                           dA_val, (int)s->nnz_img, s->img_ptr, reinterpret_cast<const int *>(s->w2),
+                                           reinterpret_cast<const float *>(s->w2 + s->val_byte_off), dC_ptr, dC_col,
+                                           dC_val, capacity);
+        if (rc)
+            s->err = mhb_last_error(s->h);
+        return rc;
+    }
+    int mhb_shard_spgemm_into_end(mhb_shard_t s, long long *nnzC)
+    {
+        if (!s)
+            return MHB_ERR_ARG;
+        int rc = mhb_spgemm_into_end(s->h, nnzC);
+        if (rc)
+            s->err = mhb_last_error(s->h);
+        return rc;
+    }
+
     int mhb_shard_post_size(mhb_shard_t s, long long nnzC_local)
     {
-        if (!s || s->phase < 2 || nnzC_local < 0)
+        if (!s || s->phase < 2 || nnzC_local < -1)
             return sfail(s, MHB_ERR_ARG, "mhb_shard_post_size: bad argument");
         ++s->size_epoch;
+        if (nnzC_local == -1)
+        {
+            // from the device: nnz(C) of the call queued by mhb_shard_spgemm_into_begin_*
+            const long long *d_nnz = nullptr;
+            const int *d_gate = nullptr;
+            if (mhb_get_device_scalars(s->h, &d_nnz, &d_gate) != MHB_OK || !d_nnz)
+                return sfail(s, MHB_ERR_ARG, "mhb_shard_post_size(-1): no SpGEMM queued on the handle");
+            k_shard_post_dev<<<1, 32, 0, stream_of(s)>>>(s->pm, s->world, s->rank, d_nnz, d_gate, s->size_epoch);
+        }
+        else
+            k_shard_post<<<1, 32, 0, stream_of(s)>>>(s->pm, s->world, s->rank, (unsigned long long)nnzC_local, s->size_epoch);
+        SCU(cudaGetLastError());
+        return MHB_OK;
+    }
+    int mhb_shard_repost_size(mhb_shard_t s, long long nnzC_local)
+    {
+        if (!s || s->phase < 2 || nnzC_local < 0 || s->size_epoch == 0)
+            return sfail(s, MHB_ERR_ARG, "mhb_shard_repost_size: bad argument or nothing posted yet");
         k_shard_post<<<1, 32, 0, stream_of(s)>>>(s->pm, s->world, s->rank, (unsigned long long)nnzC_local, s->size_epoch);
         SCU(cudaGetLastError());
         return MHB_OK;

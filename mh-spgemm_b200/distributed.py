@@ -401,8 +401,31 @@ class Shard:
         self._chk(rc)
         return int(nnz.value)
 
+    def spgemm_into_begin(self, r_lo: int, r_hi: int, dA_val, dC_ptr, dC_col, dC_val):
+        f = (self.L.mhb_shard_spgemm_into_begin_f64 if self.val_dtype.itemsize == 8
+             else self.L.mhb_shard_spgemm_into_begin_f32)
+        cap = min(dC_col.numel(), dC_val.numel()) if dC_col is not None else 0
+        self._chk(f(self.s, r_lo, r_hi, dA_val.data_ptr(), dC_ptr.data_ptr(), dC_col.data_ptr() if cap else None,
+                    dC_val.data_ptr() if cap else None, cap))
+
+    def spgemm_into_end(self) -> int:
+        from .api import ERR_CAPACITY
+        nnz = self.C.c_longlong()
+        rc = self.L.mhb_shard_spgemm_into_end(self.s, self.C.byref(nnz))
+        if rc == ERR_CAPACITY:
+            e = self.MhbError(rc, self.L.mhb_shard_last_error(self.s).decode())
+            e.nnzC = int(nnz.value)
+            raise e
+        self._chk(rc)
+        return int(nnz.value)
+
     def post_size(self, nnz_local: int):
+        """nnz_local = -1: post the device-side nnz(C) of the SpGEMM just queued by spgemm_into_begin."""
         self._chk(self.L.mhb_shard_post_size(self.s, int(nnz_local)))
+
+    def repost_size(self, nnz_local: int):
+        """Confirm (or, after a redo, supply) the size of the step already posted from the device."""
+        self._chk(self.L.mhb_shard_repost_size(self.s, int(nnz_local)))
 
     def offsets(self):
         """(offset of this rank's slice in the global col / val arrays, total nnz(C), all sizes)."""

@@ -50,6 +50,20 @@ def fem3d(nx: int = 8, ny: int = 8, nz: int = 325, dof: int = 3, seed: int = 1, 
     return CSR.from_coo(nn * dof, nn * dof, rows, cols, rng=np.random.default_rng(seed), dtype=dtype)
 
 
+def fem3d_perturbed(nx: int = 8, ny: int = 8, nz: int = 325, dof: int = 3, drop: float = 0.10, seed: int = 1,
+                    dtype=np.float64) -> CSR:
+    """fem3d with `drop` of its off-diagonal entries removed at random (diagonal kept): the dof
+    rows of a node are no longer exact twins and the runs of a row are ragged -- the cant-like
+    shape without the regularity the twin-row kernels key on ("best-case-only")."""
+    A = fem3d(nx, ny, nz, dof, seed, dtype)
+    rng = np.random.default_rng(seed + 1000)
+    rows = np.repeat(np.arange(A.M, dtype=np.int64), np.diff(A.ptr))
+    keep = (rng.random(A.nnz) >= drop) | (rows == A.col)
+    ptr = np.zeros(A.M + 1, np.int64)
+    np.cumsum(np.bincount(rows[keep], minlength=A.M), out=ptr[1:])
+    return CSR(A.M, A.N, ptr, A.col[keep], A.val[keep])
+
+
 def rmat(scale: int = 20, n: int = 1_000_005, draws: int = 3_300_000, a: float = 0.48, b: float = 0.17,
          c: float = 0.17, seed: int = 2, dtype=np.float64) -> CSR:
     """R-MAT edges on a 2^scale grid, cut to n rows/cols, duplicates merged

@@ -40,6 +40,7 @@ INPUTS = {
     "rect": lambda: (G.uniform_random(200, 300, 2000, seed=2), G.uniform_random(300, 5000, 9000, seed=3)),
     "poisson32": lambda: (G.poisson2d(32), None),
     "fem": lambda: (G.fem3d(4, 4, 10, 3, seed=5), None),
+    "fem_perturbed": lambda: (G.fem3d_perturbed(4, 4, 10, 3, drop=0.10, seed=5), None),
     "rmat14": lambda: (G.rmat(14, 16000, 60000, seed=6), None),
     "dense_rows": lambda: (G.with_dense_rows(G.uniform_random(3000, 3000, 30000, seed=8), 6, 1500, seed=9), None),
     "banded": lambda: (G.banded_random(5000, 12, 300, seed=10), None),
@@ -672,6 +673,14 @@ def test_fused_call_into_caller_buffers(orc, name, dtype):
     Cp2, Cc2, Cv2 = orc.spgemm(A2, B2)
     assert_matches(orc, C, Cp2, Cc2, Cv2)
     assert st["intprod"] == orc.intprod(A, B) and st["gpu_launches"] > 0 and t.timing.Numeric > 0
+    # the same call in its two halves (begin queues, end waits and verifies)
+    dA = [api.DeviceArray(x) for x in (A.ptr, A.col, A.val)]
+    dB = dA if B is A else [api.DeviceArray(x) for x in (B.ptr, B.col, B.val)]
+    t.spgemm_into_begin(A.M, A.N, B.N, dA[0], dA[1], dA[2], dB[0], dB[1], dB[2], dC[0], dC[1], dC[2])
+    assert t.spgemm_into_end() == Cp[-1] and t.stats["fused_calls"] == 2
+    assert_matches(orc, CSR(A.M, B.N, dC[0].numpy()[:A.M + 1], dC[1].numpy()[:nnz], dC[2].numpy()[:nnz]), Cp, Cc, Cv)
+    with pytest.raises(api.MhbError):
+        t.spgemm_into_end()  # no begin outstanding
     # pattern reuse after a fused call
     dA2v = api.DeviceArray(A.val)
     dBv = dA2v if B is A else api.DeviceArray(B.val)

@@ -73,3 +73,18 @@ def test_csr_rows_transpose_from_coo():
     bad = CSR(1, 5, np.array([0, 2], np.int32), np.array([3, 1], np.int32), np.ones(2))
     dup = CSR(1, 5, np.array([0, 2], np.int32), np.array([2, 2], np.int32), np.ones(2))
     assert not bad.is_canonical() and not dup.is_canonical()
+
+
+def test_perturbed_fem_breaks_the_twins():
+    """fem3d_perturbed keeps the cant-like shape (diagonal intact, ~10 % of the rest dropped) but no
+    two consecutive rows share a column list any more."""
+    A, P = G.fem3d(4, 4, 12, 3, seed=3), G.fem3d_perturbed(4, 4, 12, 3, drop=0.10, seed=3)
+    assert P.is_canonical() and (P.M, P.N) == (A.M, A.N)
+    assert 0.86 * A.nnz < P.nnz < 0.94 * A.nnz
+    rows = np.repeat(np.arange(P.M), np.diff(P.ptr))
+    assert int((rows == P.col).sum()) == P.M  # the diagonal survives
+    twins = lambda X: sum(np.array_equal(X.col[X.ptr[r - 1]:X.ptr[r]], X.col[X.ptr[r]:X.ptr[r + 1]])  # noqa: E731
+                          for r in range(1, X.M))
+    assert twins(A) == A.M // 3 * 2 and twins(P) < A.M // 50
+    Q = G.fem3d_perturbed(4, 4, 12, 3, drop=0.10, seed=3)
+    assert np.array_equal(P.col, Q.col) and np.array_equal(P.val, Q.val)  # seeded
