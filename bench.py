@@ -399,6 +399,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suite", action="store_true", help="skip the 12-matrix breadth check (N=1, workload F only)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="mhb_set_option on the handle before the run (A/B measurements), e.g. --opt compact_rows=0")
     ap.add_argument("--no-perturbed", action="store_true", help="skip the perturbed-FEM side measurement (N=1, workload F)")
     ap.add_argument("--contract", default="fused", choices=["fused", "two-phase"],
                     help="'fused' = mhb_spgemm_into_* (C arrays kept by the caller, one host synchronisation per "
@@ -469,6 +471,9 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     tool.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        key, _, val = kv.partition("=")
+        tool.set_option(key, int(val))
     dt = torch.float64
     a_ptr, a_col, a_val = (torch.from_numpy(Ablk.ptr).to(dev), torch.from_numpy(Ablk.col).to(dev),
                            torch.from_numpy(Ablk.val).to(dev))
@@ -844,6 +849,7 @@ def main():
             "l2": L2_NOTE, "parallelism": par,
             "call": ("mhb_spgemm_into_f64: caller-owned C arrays kept across steps, one host synchronisation per SpGEMM"
                      if fused else "mhb_symbolic + mhb_numeric_f64: two calls, host reads nnz(C) in between"),
+            "options": args.opt or None,
             "fused_calls": stats.get("fused_calls"), "speculative_misses": stats.get("speculative_misses"),
             "timed_region": ("start event | exchange, every kernel of the SpGEMM, slice-size post | stop event, all queued "
                              "before the host waits (mhb_spgemm_into_begin / _end)" if device_bracket else

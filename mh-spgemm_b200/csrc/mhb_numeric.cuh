@@ -1503,26 +1503,35 @@ __global__ void __launch_bounds__(kTinyRowThreads)
         const int cap = __ldg(&Cp[row + 1]) - out; // <= NB_TINY_MAX by the bin's definition
         int n = 0;
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j = s; j < e; ++j)
+        // ONE loop over the products of the row (the nested form -- for every nonzero of A, for every
+        // entry of its B row -- reconverges the warp at the end of every B row, so a warp paid the
+        // longest B row of every round: 5.6 of 32 lanes active on the power-law input, r2n)
+        int j = s, q = 0, qe = 0;
+        T a = T(0);
+        while (true)
         {
-            const int k = __ldg(&Ac[j]);
-            const T a = __ldg(&Av[j]);
-            const int qs = __ldg(&Bp[k]), qe = __ldg(&Bp[k + 1]);
-            for (int q = qs; q < qe; ++q)
+            while (q == qe && j < e) // next nonzero of A (skipping empty B rows)
             {
-                const int c = __ldg(&Bc[q]);
-                const T x = a * __ldg(&Bv[q]);
-                int p = 0;
-                while (p < n && keys[p * kTinyRowThreads + t] != c)
-                    ++p;
-                if (p < n)
-                    vals[p * kTinyRowThreads + t] += x;
-                else if (n < cap)
-                {
-                    keys[n * kTinyRowThreads + t] = c;
-                    vals[n * kTinyRowThreads + t] = x;
-                    ++n;
-                }
+                const int k = __ldg(&Ac[j]);
+                a = __ldg(&Av[j]);
+                q = __ldg(&Bp[k]), qe = __ldg(&Bp[k + 1]);
+                ++j;
+            }
+            if (q == qe)
+                break;
+            const int c = __ldg(&Bc[q]);
+            const T x = a * __ldg(&Bv[q]);
+            ++q;
+            int p = 0;
+            while (p < n && keys[p * kTinyRowThreads + t] != c)
+                ++p;
+            if (p < n)
+                vals[p * kTinyRowThreads + t] += x;
+            else if (n < cap)
+            {
+                keys[n * kTinyRowThreads + t] = c;
+                vals[n * kTinyRowThreads + t] = x;
+                ++n;
             }
         }
         for (int i = 1; i < n; ++i) // insertion sort by column

@@ -444,25 +444,32 @@ __global__ void __launch_bounds__(kTinyThreads)
         const int row = rows[r];
         int n = 0;
         const int s = __ldg(&Ap[row]), e = __ldg(&Ap[row + 1]);
-        for (int j = s; j < e; ++j)
+        // one loop over the tile visits of the row (see k_num_tiny: the nested form reconverges the
+        // warp at the end of every B row)
+        int j = s, q = 0, qe = 0;
+        while (true)
         {
-            const int k = __ldg(&Ac[j]);
-            const int qs = __ldg(&tileptr[k]), qe = __ldg(&tileptr[k + 1]);
-            for (int q = qs; q < qe; ++q)
+            while (q == qe && j < e)
             {
-                const int tc = __ldg(&tilecol[q]);
-                const unsigned m = __ldg(&tilemask[q]);
-                int p = 0;
-                while (p < n && keys[p * kTinyThreads + t] != tc)
-                    ++p;
-                if (p < n)
-                    masks[p * kTinyThreads + t] |= m;
-                else
-                {
-                    keys[n * kTinyThreads + t] = tc;
-                    masks[n * kTinyThreads + t] = m;
-                    ++n;
-                }
+                const int k = __ldg(&Ac[j]);
+                q = __ldg(&tileptr[k]), qe = __ldg(&tileptr[k + 1]);
+                ++j;
+            }
+            if (q == qe)
+                break;
+            const int tc = __ldg(&tilecol[q]);
+            const unsigned m = __ldg(&tilemask[q]);
+            ++q;
+            int p = 0;
+            while (p < n && keys[p * kTinyThreads + t] != tc)
+                ++p;
+            if (p < n)
+                masks[p * kTinyThreads + t] |= m;
+            else
+            {
+                keys[n * kTinyThreads + t] = tc;
+                masks[n * kTinyThreads + t] = m;
+                ++n;
             }
         }
         int c = 0;
