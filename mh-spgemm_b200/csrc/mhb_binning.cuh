@@ -202,9 +202,13 @@ template <int G>
 __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restrict__ Ap, const int *__restrict__ Ac,
                                                       const int4 *__restrict__ binfo, int4 *__restrict__ arow,
                                                       unsigned char *__restrict__ binid, int *__restrict__ counts,
-                                                      int *__restrict__ scal, int force_path)
+                                                      int *__restrict__ scal, int force_path,
+                                                      const unsigned char *__restrict__ twins)
 {
     pdl_prologue();
+    // twins (optional): twins[r] != 0 when row r has the column list of row r-1 (multi-dof FEM).  Such
+    // a row has the metrics of its run's first row: only run leaders are computed, and the group that
+    // computed a leader writes the followers' records too.
     constexpr int kLong = 32 * G; // rows longer than this are walked by the whole warp
     constexpr int GPW = 32 / G;   // rows per warp and step
     __shared__ long long sh_ip[8], sh_tf[8];
@@ -219,8 +223,9 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
     for (long long base = warp0 * GPW; base < M; base += nwarps * GPW)
     {
         const long long gid = base + lane_id() / G;
-        const bool valid = gid < M;
-        const int row = valid ? (int)gid : 0;
+        const bool in_range = gid < M;
+        const int row = in_range ? (int)gid : 0;
+        const bool valid = in_range && !(twins && row > 0 && __ldg(&twins[row])); // followers are written by their leader
         int s = 0, e = 0;
         if (valid)
         {
@@ -257,15 +262,20 @@ __global__ void __launch_bounds__(256) k_arow_metrics(int M, const int *__restri
         if (valid && l == 0)
         {
             const int ip = sat_i32(a.ip), tf = sat_i32(a.tf);
-            arow[row] = make_int4(ip, tf, a.cmin, a.cmax);
             const int b = mhb_classify_sym(ip, tf, a.cmin, a.cmax, force_path);
-            binid[row] = (unsigned char)b;
-            if (b == SB_EMPTY)
-                counts[row] = 0;
             if (row == 0)
                 counts[M] = 0;
-            ip_tot += a.ip;
-            tf_tot += a.tf;
+            int r2 = row;
+            do // the row and the twins that follow it
+            {
+                arow[r2] = make_int4(ip, tf, a.cmin, a.cmax);
+                binid[r2] = (unsigned char)b;
+                if (b == SB_EMPTY)
+                    counts[r2] = 0;
+                ip_tot += a.ip;
+                tf_tot += a.tf;
+                ++r2;
+            } while (twins && r2 < M && __ldg(&twins[r2]));
             tf_max = max(tf_max, tf);
         }
     }

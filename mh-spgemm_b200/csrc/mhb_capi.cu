@@ -926,12 +926,14 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     if (M > 0)
     {
         double avg = (double)nnzA / M;
+        // twin flags of A's rows, when they are known this early: B's flags (family 1) if A is B
+        const unsigned char *tw = (h->sym_twins && Ap == Bp && Ac == Bc) ? h->bsame.as<unsigned char>() : nullptr;
         if (avg > 12.0)
             LAUNCH(h, k_arow_metrics<32>, std::min(cdiv((long long)M * 32, 256), h->num_sms * 16), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
-                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
+                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym, tw);
         else
             LAUNCH(h, k_arow_metrics<4>, std::min(cdiv((long long)M * 4, 256), h->num_sms * 16), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
-                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym);
+                   h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym, tw);
     }
     else
         CU(cudaMemsetAsync(Cp, 0, sizeof(int), h->stream));
