@@ -109,6 +109,32 @@ def main():
             barrier(sh)  # nobody may still be pulling when the next step rewrites the shard
             for d in (dCp, dCc, dCv):
                 d.free()
+        # the fused call through the shard layer (mhb_shard_spgemm_into_begin / _end): caller-owned C
+        # arrays, slice size posted from the DEVICE behind the kernels and confirmed after the host
+        # read; the second step runs with a single host synchronisation
+        cap = max(int(Cp[-1]), 1)
+        dCp = api.DeviceArray(count=Ablk.M + 1, dtype=np.int32)
+        dCc, dCv = api.DeviceArray(count=cap, dtype=np.int32), api.DeviceArray(count=cap, dtype=A.val.dtype)
+        fused0 = tool.stats["fused_calls"]
+        for step in range(2):
+            exchange(sh)
+            sh.spgemm_into_begin(0, Ablk.M, dAv, dCp, dCc, dCv)
+            sh.post_size(-1)
+            nnz = sh.spgemm_into_end()
+            sh.repost_size(nnz)
+            if shared:
+                host_fence()
+            off, tot, sizes = sh.offsets()
+            cp, cc, cv = dCp.numpy(), dCc.numpy()[:nnz], dCv.numpy()[:nnz]
+            assert nnz == int(Cp[-1]) and np.array_equal(cp.astype(np.int64), Cp) and np.array_equal(cc, Cc), \
+                f"{name} rank {rank}: fused structure differs"
+            bad, first = orc.compare(Ablk.M, (cp, cc, cv), (Cp, Cc, Cv * A.val.dtype.type(3.0)), rtol)
+            assert bad == 0, f"{name} rank {rank} fused step {step}: {bad} values out of tolerance (first {first})"
+            assert off == int(gp[r0]) and tot == int(gp[-1]), (off, tot)
+            barrier(sh)
+        assert tool.stats["fused_calls"] >= fused0 + 1, tool.stats
+        for d in (dCp, dCc, dCv):
+            d.free()
         # the rows of a rank cut into two slices after ONE exchange (the int32-overflow path)
         if Ablk.M >= 2:
             exchange(sh)
