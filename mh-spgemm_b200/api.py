@@ -24,7 +24,7 @@ from .csr import CSR
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmhb_spgemm.so")
 
-SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M"]
+SYM_BINS = ["EMPTY", "BM_G8", "BM_WARP", "BM_BLOCK", "H_G8", "H_WARP", "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M", "H_G16"]
 NUM_BINS = ["EMPTY", "WIN_G8", "WIN_WARP", "WIN_BLOCK_S", "WIN_BLOCK_L", "H_G8", "H_WARP_S", "H_WARP_L",
             "H_BLOCK_S", "H_BLOCK_L", "H_GLOBAL", "TINY", "TINY_S", "TINY_M", "H_WARP_XS", "H_WARP_M", "WIN_COMPACT",
             "H_BLOCK_M", "H_BLOCK_XS"]

@@ -539,6 +539,14 @@ int launch_symbolic_bins(mhb_context *h, bool spec)
                GPB * 2 * SB_H_WARP_SLOTS * 4, list(SB_H_WARP), h->Ap, h->Ac, tp, tc, tm, arow, counts,
                log2_ceil(SB_H_WARP_SLOTS), scal, probes);
     }
+    if ((n = n_of(SB_H_G16)) > 0)
+    {
+        constexpr int G = 16, GPB = kSymThreads / G;
+        if (int e_ = next_bin_stream(h, &st)) return e_;
+        LAUNCH_ON(h, st, k_sym_hash_group<G>, std::min(cdiv(n, GPB), cap_blocks), kSymThreads,
+               GPB * 2 * SB_H_G16_SLOTS * 4, list(SB_H_G16), h->Ap, h->Ac, tp, tc, tm, arow, counts,
+               log2_ceil(SB_H_G16_SLOTS), scal, probes);
+    }
     if ((n = n_of(SB_BM_WARP)) > 0)
     {
         constexpr int G = 32, GPB = kSymThreads / G;

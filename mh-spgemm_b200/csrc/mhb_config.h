@@ -34,6 +34,8 @@ enum MhbSymBin
                     // over rows sorted by class: the threads of a warp then carry rows of similar cost (on
                     // power-law inputs the rows of the old single bin differed 100x in cost and a warp ran
                     // 4 of its 32 lanes, profiles/r2l_hash_kernels_R.md)
+    SB_H_G16,       // tile hash, 16 lanes/row, ub <= 96 (256 slots): two rows per warp share the per-row
+                    // fixed cost (~600 warp instructions) that dominates rows this short
     SB_COUNT
 };
 #define SB_BM_G8_WORDS 64
@@ -41,6 +43,8 @@ enum MhbSymBin
 #define SB_BM_BLOCK_WORDS 57344
 #define SB_H_G8_SLOTS 32
 #define SB_H_G8_MAX 24
+#define SB_H_G16_SLOTS 256
+#define SB_H_G16_MAX 96
 #define SB_H_WARP_SLOTS 512
 #define SB_H_WARP_MAX 384
 #define SB_H_BLOCK_S_SLOTS 4096
@@ -138,6 +142,8 @@ MHB_HD int mhb_classify_sym(int ip, int tf, int cmin, int cmax, int force)
     long long ub = wt < tf ? wt : tf;
     if (ub <= SB_H_G8_MAX)
         return SB_H_G8;
+    if (ub <= SB_H_G16_MAX)
+        return SB_H_G16;
     if (ub <= SB_H_WARP_MAX)
         return SB_H_WARP;
     if (ub <= SB_H_BLOCK_S_MAX)

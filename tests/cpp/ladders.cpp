@@ -72,6 +72,7 @@ int main()
                     case SB_BM_WARP: CHECK(wt <= SB_BM_WARP_WORDS); break;
                     case SB_BM_BLOCK: CHECK(wt <= SB_BM_BLOCK_WORDS && wt * 4 <= MHB_SMEM_MAX); break;
                     case SB_H_G8: CHECK(ub <= SB_H_G8_MAX && ub * 4 <= SB_H_G8_SLOTS * 3); break;
+                    case SB_H_G16: CHECK(ub <= SB_H_G16_MAX && ub * 4 <= SB_H_G16_SLOTS * 3); break;
                     case SB_H_WARP: CHECK(ub <= SB_H_WARP_MAX && ub * 4 <= SB_H_WARP_SLOTS * 3); break;
                     case SB_H_BLOCK_S: CHECK(ub <= SB_H_BLOCK_S_MAX && ub * 4 <= SB_H_BLOCK_S_SLOTS * 3); break;
                     case SB_H_BLOCK_L: CHECK(ub <= SB_H_BLOCK_L_MAX && ub * 4 <= SB_H_BLOCK_L_SLOTS * 3); break;
