@@ -372,6 +372,37 @@ __global__ void k_fused_gate(int *__restrict__ scal, unsigned sym_launched, int 
     scal[SC_GATE] = g;
 }
 
+// Host-buffer path: the numeric phase is cut into row chunks so that the download of a finished
+// chunk of C overlaps the computation of the next.  A bin's row list is ascending, so the rows of
+// chunk c (rows [r[c], r[c+1]) of the matrix) are a contiguous piece of every bin's list: this
+// kernel finds its ends by binary search.  out[b * (nc + 1) + c] = first position (in the
+// concatenated bin array) of bin b whose row is >= r[c].
+constexpr int kMaxRowChunks = 8;
+struct ChunkRows
+{
+    int r[kMaxRowChunks + 1];
+};
+__global__ void k_chunk_bounds(const int *__restrict__ bins, const int *__restrict__ off, int nbins, int nc, ChunkRows rows,
+                               int *__restrict__ out)
+{
+    pdl_prologue();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbins * (nc + 1))
+        return;
+    const int b = t / (nc + 1), c = t % (nc + 1);
+    int lo = off[b], hi = off[b + 1];
+    const int target = rows.r[c];
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (bins[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[t] = lo;
+}
+
 // ---------------------------------------------------------------------------------------
 // Stable binning: count per block, scan per bin across blocks on the device, scatter with
 // warp-level ranks (match_any + popc) and a warp prefix in shared memory.

@@ -128,6 +128,8 @@ struct mhb_context
     int num_sms = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_vals = nullptr, ev_ready = nullptr;
+    cudaEvent_t ev_chunk[kMaxRowChunks] = {nullptr}; // host-buffer path: numeric row chunk c is complete
+    int row_chunks = 4;                              // option "row_chunks": chunks of the host path (1: off)
     static constexpr int kAux = 5; // per-bin kernels of one phase run concurrently (the reference uses 12 streams)
     cudaStream_t aux[kAux] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
@@ -175,6 +177,7 @@ struct mhb_context
     // host-API staging
     DevBuf sA_ptr, sA_col, sA_val, sB_ptr, sB_col, sB_val, sC_ptr, sC_col, sC_val;
     DevBuf tr_key[2], tr_idx[2], tr_hist; // radix-sort scratch of mhb_transpose_*
+    DevBuf chunk_off;                     // [bins][chunks + 1] positions in bins_num (host-buffer path)
     HostBuf hC_ptr, hC_col, hC_val;
     cudaEvent_t ev[EV_COUNT] = {nullptr};
     bool ev_sym_valid = false, ev_num_valid = false;
@@ -602,8 +605,11 @@ size_t hash_list_smem(int S)
 }
 
 template <typename T>
-int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool spec = false)
+int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool spec = false,
+                        const int *chunk_off = nullptr, int chunk = 0, int nchunks = 1)
 {
+    // chunk_off (host-buffer path): launch only the rows of row chunk `chunk`; the piece of every
+    // bin's list comes from the device-side table k_chunk_bounds filled
     // spec: the fused call (do_spgemm_into) has not read this call's bin sizes; h->num_off and
     // h->max_rownnz are the previous call's and only size grids and scratch, the kernels take
     // their ranges from the device-side offsets and stand down when the capacity gate is set
@@ -611,6 +617,8 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     auto n_of = [&](int b) { return off[b + 1] - off[b]; };
     const int *bins = h->bins_num.as<int>();
     auto list = [&](int b) {
+        if (chunk_off)
+            return RowList{bins, chunk_off + b * (nchunks + 1) + chunk, -1, nullptr};
         return spec ? RowList{bins, h->scal.as<int>() + SC_NUM_OFF + b, -1, h->scal.as<int>() + SC_GATE}
                     : RowList{bins + off[b], nullptr, n_of(b), nullptr};
     };
@@ -829,10 +837,20 @@ int launch_numeric_bins(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv
     if ((n = off[NB_TINY + 3] - off[NB_TINY]) > 0)
     {
         if (int e_ = next_bin_stream(h, &st)) return e_;
-        RowList tl = spec ? RowList{bins, scal + SC_NUM_OFF + NB_TINY, -1, scal + SC_GATE, 3}
-                          : RowList{bins + off[NB_TINY], nullptr, n, nullptr, 1};
-        LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
-                  NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4), tl, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+        if (chunk_off) // a row chunk is a separate piece of each class's list: one launch per class
+        {
+            for (int tb = NB_TINY; tb < NB_TINY + 3; ++tb)
+                if (n_of(tb) > 0)
+                    LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n_of(tb), kTinyRowThreads), cap_blocks), kTinyRowThreads,
+                              NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4), list(tb), Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+        }
+        else
+        {
+            RowList tl = spec ? RowList{bins, scal + SC_NUM_OFF + NB_TINY, -1, scal + SC_GATE, 3}
+                              : RowList{bins + off[NB_TINY], nullptr, n, nullptr, 1};
+            LAUNCH_ON(h, st, k_num_tiny<T>, std::min(cdiv(n, kTinyRowThreads), cap_blocks), kTinyRowThreads,
+                      NB_TINY_MAX * kTinyRowThreads * (sizeof(T) + 4), tl, Ap, Ac, Av, Bp, Bc, Bv, Cp, Cc, Cv);
+        }
     }
     return join_bins(h);
 }
@@ -1368,15 +1386,66 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
     CUD(h->hC_col.ensure(n * 4));
     CUD(h->hC_val.ensure(n * sizeof(T)));
     CUD(cudaMemcpyAsync(h->hC_ptr.p, h->sC_ptr.p, ((size_t)M + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
-    rc = do_numeric<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false);
-    if (rc)
-        return drain(rc);
-    CUD(cudaMemcpyAsync(h->hC_col.p, h->sC_col.p, (size_t)*nnzC * 4, cudaMemcpyDeviceToHost, st));
-    CUD(cudaMemcpyAsync(h->hC_val.p, h->sC_val.p, (size_t)*nnzC * sizeof(T), cudaMemcpyDeviceToHost, st));
+    // The download of C is most of this call (PCIe: 12 bytes per entry).  With enough of it, the
+    // numeric phase runs in row chunks balanced by nnz and the copy of a finished chunk (on
+    // copy_stream) overlaps the computation of the next: the tail of the call is then the download
+    // alone instead of numeric + download.
+    const int nc = (h->row_chunks > 1 && (size_t)*nnzC * (4 + sizeof(T)) >= ((size_t)32 << 20) && M >= 4096)
+                       ? std::min(h->row_chunks, (int)kMaxRowChunks)
+                       : 1;
+    if (nc > 1)
+    {
+        CUD(cudaStreamSynchronize(st)); // C.ptr is on the host: chunk bounds and byte ranges come from it
+        const int *hp = h->hC_ptr.as<int>();
+        ChunkRows cr;
+        cr.r[0] = 0;
+        for (int c = 1; c < nc; ++c)
+        {
+            const long long want = *nnzC * c / nc;
+            int r = (int)(std::lower_bound(hp, hp + M + 1, (int)std::min<long long>(want, INT_MAX)) - hp);
+            cr.r[c] = std::max(cr.r[c - 1], std::min(r, M));
+        }
+        for (int c = nc; c <= (int)kMaxRowChunks; ++c)
+            cr.r[c] = M;
+        CUD(h->chunk_off.ensure((size_t)MHB_MAX_BINS * (kMaxRowChunks + 1) * 4));
+        LAUNCH(h, k_chunk_bounds, cdiv((long long)NB_COUNT * (nc + 1), 128), 128, 0, (const int *)h->bins_num.as<int>(),
+               (const int *)(h->scal.as<int>() + SC_NUM_OFF), (int)NB_COUNT, nc, cr, h->chunk_off.as<int>());
+        CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
+        CUD(cudaEventRecord(h->ev[EV_NUM0], st));
+        for (int c = 0; c < nc; ++c)
+        {
+            rc = launch_numeric_bins<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false,
+                                        h->chunk_off.as<int>(), c, nc);
+            if (rc)
+                return drain(rc);
+            CUD(cudaEventRecord(h->ev_chunk[c], st));
+            CUD(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[c], 0));
+            const size_t e0 = (size_t)hp[cr.r[c]], e1 = (size_t)hp[cr.r[c + 1]];
+            if (e1 > e0)
+            {
+                CUD(cudaMemcpyAsync(h->hC_col.as<int>() + e0, h->sC_col.as<int>() + e0, (e1 - e0) * 4, cudaMemcpyDeviceToHost,
+                                    h->copy_stream));
+                CUD(cudaMemcpyAsync(h->hC_val.as<T>() + e0, h->sC_val.as<T>() + e0, (e1 - e0) * sizeof(T),
+                                    cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+        }
+        CUD(cudaEventRecord(h->ev[EV_NUM1], st));
+        h->stats.gpu_launches = h->launches;
+    }
+    else
+    {
+        CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
+        rc = do_numeric<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false);
+        if (rc)
+            return drain(rc);
+        CUD(cudaMemcpyAsync(h->hC_col.p, h->sC_col.p, (size_t)*nnzC * 4, cudaMemcpyDeviceToHost, st));
+        CUD(cudaMemcpyAsync(h->hC_val.p, h->sC_val.p, (size_t)*nnzC * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
     int *hs = h->h_scal.as<int>();
     CUD(cudaMemcpyAsync(hs + SC_ERROR, h->scal.as<int>() + SC_ERROR, 6 * 4, cudaMemcpyDeviceToHost, st));
     CUD(cudaStreamSynchronize(st));
+    if (nc > 1)
+        CUD(cudaStreamSynchronize(h->copy_stream));
 #undef CUD
     rc = check_dev_error(h, hs);
     if (rc)
@@ -1500,6 +1569,9 @@ extern "C"
         for (auto &e : h->ev)
             if (cudaEventCreate(&e) != cudaSuccess)
                 return bail(MHB_ERR_CUDA);
+        for (auto &e : h->ev_chunk)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+                return bail(MHB_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess)
             return bail(MHB_ERR_CUDA);
         int prio_lo = 0, prio_hi = 0; // helper streams 0-1 (big-row bins) get the high priority
@@ -1526,11 +1598,14 @@ extern "C"
         for (DevBuf *b : {&h->flags, &h->wordprefix, &h->tileptr, &h->tilecol, &h->tilemask, &h->binfo, &h->arow,
                           &h->binid, &h->bsame, &h->asame_buf, &h->bm_store, &h->bm_slot, &h->bins_sym, &h->bins_num, &h->blockhist, &h->scan_tmp, &h->scal, &h->pool,
                           &h->sA_ptr, &h->sA_col, &h->sA_val, &h->sB_ptr, &h->sB_col, &h->sB_val, &h->sC_ptr,
-                          &h->sC_col, &h->sC_val, &h->tr_key[0], &h->tr_key[1], &h->tr_idx[0], &h->tr_idx[1], &h->tr_hist})
+                          &h->sC_col, &h->sC_val, &h->tr_key[0], &h->tr_key[1], &h->tr_idx[0], &h->tr_idx[1], &h->tr_hist, &h->chunk_off})
             b->release();
         for (HostBuf *b : {&h->h_scal, &h->hC_ptr, &h->hC_col, &h->hC_val})
             b->release();
         for (auto &e : h->ev)
+            if (e)
+                cudaEventDestroy(e);
+        for (auto &e : h->ev_chunk)
             if (e)
                 cudaEventDestroy(e);
         for (int a = 0; a < mhb_context::kAux; ++a)
@@ -1597,6 +1672,8 @@ extern "C"
             h->mask_onepass = (int)value;
         else if (k == "speculate")
             h->speculate = (int)value;
+        else if (k == "row_chunks")
+            h->row_chunks = (int)std::max<long long>(1, std::min<long long>(value, kMaxRowChunks));
         else if (k == "nnz_limit")
             h->nnz_limit = std::min<long long>(value > 0 ? value : INT_MAX, INT_MAX);
         else if (k == "serial_bins")
