@@ -382,8 +382,12 @@ struct ChunkRows
 {
     int r[kMaxRowChunks + 1];
 };
+// Bins whose kernel fuses runs of twin rows (twin_bin_a / twin_bin_b, -1: none) never get a chunk
+// boundary inside a run: the boundary moves forward past the followers (they are then computed one
+// chunk EARLIER than their download needs them).
 __global__ void k_chunk_bounds(const int *__restrict__ bins, const int *__restrict__ off, int nbins, int nc, ChunkRows rows,
-                               int *__restrict__ out)
+                               int *__restrict__ out, const unsigned char *__restrict__ twins, int twin_bin_a,
+                               int twin_bin_b)
 {
     pdl_prologue();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,6 +403,12 @@ __global__ void k_chunk_bounds(const int *__restrict__ bins, const int *__restri
             lo = mid + 1;
         else
             hi = mid;
+    }
+    if (twins && (b == twin_bin_a || b == twin_bin_b))
+    {
+        const int first = off[b], end = off[b + 1];
+        while (lo > first && lo < end && bins[lo] == bins[lo - 1] + 1 && twins[bins[lo]])
+            ++lo;
     }
     out[t] = lo;
 }

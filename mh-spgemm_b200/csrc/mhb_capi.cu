@@ -130,6 +130,7 @@ struct mhb_context
     cudaEvent_t ev_vals = nullptr, ev_ready = nullptr;
     cudaEvent_t ev_chunk[kMaxRowChunks] = {nullptr}; // host-buffer path: numeric row chunk c is complete
     int row_chunks = 4;                              // option "row_chunks": chunks of the host path (1: off)
+    long long row_chunk_bytes = 32LL << 20;          // option "row_chunk_bytes": ... used when C.col + C.val are at least this large
     static constexpr int kAux = 5; // per-bin kernels of one phase run concurrently (the reference uses 12 streams)
     cudaStream_t aux[kAux] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr};
@@ -1390,7 +1391,7 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
     // numeric phase runs in row chunks balanced by nnz and the copy of a finished chunk (on
     // copy_stream) overlaps the computation of the next: the tail of the call is then the download
     // alone instead of numeric + download.
-    const int nc = (h->row_chunks > 1 && (size_t)*nnzC * (4 + sizeof(T)) >= ((size_t)32 << 20) && M >= 4096)
+    const int nc = (h->row_chunks > 1 && *nnzC * (long long)(4 + sizeof(T)) >= h->row_chunk_bytes && M >= h->row_chunks)
                        ? std::min(h->row_chunks, (int)kMaxRowChunks)
                        : 1;
     if (nc > 1)
@@ -1409,7 +1410,8 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
             cr.r[c] = M;
         CUD(h->chunk_off.ensure((size_t)MHB_MAX_BINS * (kMaxRowChunks + 1) * 4));
         LAUNCH(h, k_chunk_bounds, cdiv((long long)NB_COUNT * (nc + 1), 128), 128, 0, (const int *)h->bins_num.as<int>(),
-               (const int *)(h->scal.as<int>() + SC_NUM_OFF), (int)NB_COUNT, nc, cr, h->chunk_off.as<int>());
+               (const int *)(h->scal.as<int>() + SC_NUM_OFF), (int)NB_COUNT, nc, cr, h->chunk_off.as<int>(), h->asame,
+               (int)NB_WIN_COMPACT, h->row_twins ? (int)NB_WIN_WARP : -1);
         CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
         CUD(cudaEventRecord(h->ev[EV_NUM0], st));
         for (int c = 0; c < nc; ++c)
@@ -1672,6 +1674,8 @@ extern "C"
             h->mask_onepass = (int)value;
         else if (k == "speculate")
             h->speculate = (int)value;
+        else if (k == "row_chunk_bytes")
+            h->row_chunk_bytes = std::max<long long>(1, value);
         else if (k == "row_chunks")
             h->row_chunks = (int)std::max<long long>(1, std::min<long long>(value, kMaxRowChunks));
         else if (k == "nnz_limit")

@@ -731,3 +731,19 @@ def test_fused_call_capacity_and_miss(orc):
     nnz, C = _into(t, A1, A1, dC, cap)  # back: A2's big-row kernels find nothing to do
     assert_matches(orc, C, Cp, Cc, Cv)
     t.release()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+@pytest.mark.parametrize("name", ["fem", "rmat14", "dense_rows", "poisson32", "rect", "ragged", "fem_perturbed"])
+def test_host_path_row_chunks(orc, name, chunks):
+    """mhb_spgemm_host_* with the numeric phase cut into row chunks whose download overlaps the next
+    chunk's computation (forced on for small inputs): same CSR as the single-piece path."""
+    A, B = INPUTS[name]()
+    B = A if B is None else B
+    t = api.Tool(0)
+    t.set_option("row_chunks", chunks)
+    t.set_option("row_chunk_bytes", 1)
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    for _ in range(2):  # second call: speculative symbolic in front of the chunked numeric
+        assert_matches(orc, t.spgemm_host(A, B), Cp, Cc, Cv)
+    t.release()
