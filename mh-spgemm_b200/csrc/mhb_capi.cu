@@ -129,7 +129,7 @@ struct mhb_context
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_vals = nullptr, ev_ready = nullptr;
     cudaEvent_t ev_chunk[kMaxRowChunks] = {nullptr}; // host-buffer path: numeric row chunk c is complete
-    int row_chunks = 4;                              // option "row_chunks": chunks of the host path (1: off)
+    int row_chunks = 2;                              // option "row_chunks": chunks of the host path (1: off)
     long long row_chunk_bytes = 32LL << 20;          // option "row_chunk_bytes": ... used when C.col + C.val are at least this large
     static constexpr int kAux = 5; // per-bin kernels of one phase run concurrently (the reference uses 12 streams)
     cudaStream_t aux[kAux] = {nullptr};
@@ -1402,7 +1402,10 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
         cr.r[0] = 0;
         for (int c = 1; c < nc; ++c)
         {
-            const long long want = *nnzC * c / nc;
+            // geometric sizes (1 : 2 : 4 ...): a small first chunk starts the download early, and few,
+            // large copies keep PCIe efficient (r2t: 8 copies of 17-34 MB cost 0.28 ms more than 2 of 67-135 MB,
+            // as much as four equal chunks gained)
+            const long long want = *nnzC * ((1LL << c) - 1) / ((1LL << nc) - 1);
             int r = (int)(std::lower_bound(hp, hp + M + 1, (int)std::min<long long>(want, INT_MAX)) - hp);
             cr.r[c] = std::max(cr.r[c - 1], std::min(r, M));
         }
@@ -1414,6 +1417,16 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
                (int)NB_WIN_COMPACT, h->row_twins ? (int)NB_WIN_WARP : -1);
         CUD(cudaStreamWaitEvent(st, h->ev_vals, 0));
         CUD(cudaEventRecord(h->ev[EV_NUM0], st));
+        // MHB_TRACE_HOST=1: device timeline of the chunks (numeric done / download done), printed after the call
+        static const bool trace = std::getenv("MHB_TRACE_HOST") != nullptr;
+        cudaEvent_t tn[kMaxRowChunks] = {nullptr}, td[kMaxRowChunks] = {nullptr}, tv = nullptr;
+        if (trace)
+        {
+            for (int c = 0; c < nc; ++c)
+                cudaEventCreate(&tn[c]), cudaEventCreate(&td[c]);
+            cudaEventCreate(&tv);
+            cudaEventRecord(tv, st); // = value upload complete (st has just waited for it)
+        }
         for (int c = 0; c < nc; ++c)
         {
             rc = launch_numeric_bins<T>(h, h->sA_val.as<T>(), dBv, h->sC_col.as<int>(), h->sC_val.as<T>(), false,
@@ -1421,6 +1434,8 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
             if (rc)
                 return drain(rc);
             CUD(cudaEventRecord(h->ev_chunk[c], st));
+            if (trace)
+                cudaEventRecord(tn[c], st);
             CUD(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[c], 0));
             const size_t e0 = (size_t)hp[cr.r[c]], e1 = (size_t)hp[cr.r[c + 1]];
             if (e1 > e0)
@@ -1430,8 +1445,29 @@ int do_spgemm_host(mhb_context *h, int M, int K, int N, const int *hAp, const in
                 CUD(cudaMemcpyAsync(h->hC_val.as<T>() + e0, h->sC_val.as<T>() + e0, (e1 - e0) * sizeof(T),
                                     cudaMemcpyDeviceToHost, h->copy_stream));
             }
+            if (trace)
+                cudaEventRecord(td[c], h->copy_stream);
         }
         CUD(cudaEventRecord(h->ev[EV_NUM1], st));
+        if (trace)
+        {
+            cudaStreamSynchronize(st);
+            cudaStreamSynchronize(h->copy_stream);
+            float a = 0.f;
+            cudaEventElapsedTime(&a, h->ev[EV_START], tv);
+            std::fprintf(stderr, "[mhb host trace] values up at %.3f ms after the first kernel;", a);
+            for (int c = 0; c < nc; ++c)
+            {
+                float n_ = 0.f, d_ = 0.f;
+                cudaEventElapsedTime(&n_, h->ev[EV_START], tn[c]);
+                cudaEventElapsedTime(&d_, h->ev[EV_START], td[c]);
+                std::fprintf(stderr, " chunk %d: numeric %.3f download %.3f (%.1f MB);", c, n_, d_,
+                             (hp[cr.r[c + 1]] - hp[cr.r[c]]) * (4.0 + sizeof(T)) / 1e6);
+                cudaEventDestroy(tn[c]), cudaEventDestroy(td[c]);
+            }
+            cudaEventDestroy(tv);
+            std::fprintf(stderr, "\n");
+        }
         h->stats.gpu_launches = h->launches;
     }
     else

@@ -1,0 +1,8 @@
+# usage: bash scripts/gpu_r2_final_scale.sh N   (under gpurun --gpus N)
+N=$1
+set -x
+O=gpurun_out/r2u
+mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 3 --no-suite --no-cpu-baseline > $O/F_n${N}_peer.json 2> $O/F_n${N}_peer.err
+timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 3 --no-suite --no-cpu-baseline --exchange broadcast > $O/F_n${N}_broadcast.json 2> $O/F_n${N}_broadcast.err
