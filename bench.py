@@ -310,8 +310,9 @@ def perturbed_fem(tool, torch, dev, steps=10) -> dict:
         torch.cuda._sleep(SPIN_CYCLES)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        nnz = tool.spgemm_into(A.M, A.N, A.N, a_ptr, a_col, a_val, a_ptr, a_col, a_val, cp, cc, cv)
+        tool.spgemm_into_begin(A.M, A.N, A.N, a_ptr, a_col, a_val, a_ptr, a_col, a_val, cp, cc, cv)
         e1.record(stream)
+        nnz = tool.spgemm_into_end()
         torch.cuda.synchronize()
         if k >= 3:
             ms.append(e0.elapsed_time(e1))
@@ -440,7 +441,24 @@ def main():
 
     # ---- workload: identical seeded matrix on every rank, rows sharded by product count ----
     strong = args.workload == "G"  # fixed matrix split over the ranks (strong scaling)
-    if strong:
+    rmat_scale = int(os.environ.get("MHB_RMAT_SCALE", "22"))
+    if strong and os.environ.get("MHB_RMAT_GEN", "device" if rmat_scale >= 23 else "host") == "device":
+        # full-size configs[4]: every rank draws the SAME matrix on its own GPU (seeded Philox stream) --
+        # the host generator needs minutes per process at scale 24 while the whole box waits
+        S = rmat_scale
+        A = G.rmat_device(S, 1 << S, 16 << S, 0.45, 0.15, 0.15, seed=5, device=dev)
+        torch.cuda.empty_cache()
+        cfg = {"workload": f"configs[4] R-MAT scale {S} ({1 << S} rows, {16 << S} draws, a=.45 b=c=.15; drawn on the device, "
+                           f"torch Philox seed 5), C=A*A, row-sharded", "rows": A.M, "nnzA": A.nnz}
+        if world > 1:  # the ranks must hold the same matrix
+            chk = torch.tensor([float(A.nnz), float(A.col[::4097].astype(np.int64).sum()), float(A.val[::4099].sum())],
+                               dtype=torch.float64, device=dev)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                raise SystemExit("device-side R-MAT differs between the ranks")
+    elif strong:
         # the large R-MAT takes the host a minute to generate: the first process to need it writes
         # it to shared memory, every other rank (and later runs on the same box) reads it back --
         # the same seeded input either way

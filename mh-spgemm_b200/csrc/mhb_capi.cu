@@ -1573,7 +1573,7 @@ int do_transpose(mhb_context *h, int M, int N, int nnz, const int *Ap, const int
 extern "C"
 {
 
-    const char *mhb_version(void) { return "mhb-spgemm 0.1 (sm_100a)"; }
+    const char *mhb_version(void) { return "mhb-spgemm 0.2 (sm_100a)"; }
 
     int mhb_create(mhb_handle_t *out, int device)
     {

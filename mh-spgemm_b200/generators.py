@@ -81,6 +81,40 @@ def rmat(scale: int = 20, n: int = 1_000_005, draws: int = 3_300_000, a: float =
     return CSR.from_coo(n, n, r[keep], cidx[keep], rng=rng, dtype=dtype)
 
 
+def rmat_device(scale: int, n: int, draws: int, a: float, b: float, c: float, seed: int, device, dtype=np.float64) -> CSR:
+    """The same R-MAT recipe drawn and canonicalised with torch on `device` (Philox stream of a seeded
+    torch.Generator, so every rank of a job gets the same matrix without shipping it): what makes the
+    full-size BASELINE configs[4] (scale 24: 268 M draws) practical -- numpy needs minutes per process for
+    it while an 8-GPU box waits.  A DIFFERENT random stream than rmat(): the two give different matrices of
+    the same distribution.  Returns host arrays (the bench partitions on the host)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    r = torch.zeros(draws, dtype=torch.int32, device=dev)
+    ci = torch.zeros(draws, dtype=torch.int32, device=dev)
+    for _ in range(scale):
+        u = torch.rand(draws, generator=g, device=dev, dtype=torch.float32)
+        rbit = u >= a + b
+        cbit = ((u >= a) & (u < a + b)) | (u >= a + b + c)
+        r = (r << 1) | rbit.to(torch.int32)
+        ci = (ci << 1) | cbit.to(torch.int32)
+        del u, rbit, cbit
+    keep = (r < n) & (ci < n)
+    key = r[keep].to(torch.int64) * n + ci[keep].to(torch.int64)
+    del r, ci, keep
+    key = torch.unique(key)  # sorted, duplicates merged
+    rows = key // n
+    cols = (key - rows * n).to(torch.int32)
+    del key
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0)
+    del rows
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    vals = torch.rand(cols.numel(), generator=g, device=dev, dtype=tdt) + 0.5
+    return CSR(n, n, ptr.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy().astype(dtype, copy=False))
+
+
 def banded_random(M: int, per_row: int, halfband: int, seed: int = 3, dtype=np.float64) -> CSR:
     """Near-regular random rows with locality (cage/mac_econ-like): per_row draws per row
     within +-halfband of the diagonal, plus the diagonal."""
