@@ -1293,7 +1293,14 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         // sort below is left.  On power-law graphs that is most rows (webbase-like input: 94 % of the
         // rows of these bins, 57 % of all products).
         const bool uniq = info.x == n;
-        if (uniq)
+        // ... and a row with FEW repeated columns (products <= the entries the bin's arrays hold) goes the
+        // same way -- expand, sort, compress: the sort below then ranks equal columns by position, marks
+        // the first of each as its head, and the others are added onto their head's entry of C.  Banded
+        // random / power-law rows have compression 1.00-1.05: nearly all of them qualify.
+        const bool esc = !uniq && info.x > n && info.x <= nmax;
+        const bool direct = uniq || esc;
+        const int ne = direct ? info.x : n; // entries to sort
+        if (direct)
             walk_flat_indexed<32, T, T>(kFull, lane, s, e, warp, nwarp, Ac, Av, Bp, Bc, Bv, [&](int pos, int c, T v, T a) {
                 keys[pos] = c;
                 vals[pos] = a * v;
@@ -1398,17 +1405,99 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         }
         else
             clustered = __syncthreads_or(mx > kBucketMax);
-        if (!clustered)
+        if (!clustered || esc)
         {
-            for (int i = tid; i < n; i += nthr)
+            for (int i = tid; i < ne; i += nthr)
             {
-                const unsigned short sl = uniq ? (unsigned short)i : list[i];
+                const unsigned short sl = direct ? (unsigned short)i : list[i];
                 const int k = keys[sl];
                 const int pos = atomicAdd(&start[(k - cmin) >> sh], 1); // start[b] ends as the END of bucket b
                 idx[pos] = sl;
                 bkey[pos] = k;
             }
             bar();
+            if (esc)
+            {
+                // stable rank (column, then position) of every product; heads = first of their column
+                unsigned *hb = reinterpret_cast<unsigned *>(vals + nmax); // head bits | heads in front of each word
+                const int nW = (ne + 31) >> 5;
+                int *hpre = reinterpret_cast<int *>(hb + nW);
+                for (int w = tid; w < nW; w += nthr)
+                    hb[w] = 0u;
+                bar();
+                for (int p = tid; p < ne; p += nthr)
+                {
+                    const int k = bkey[p];
+                    const int b = (k - cmin) >> sh;
+                    const int lo = b ? start[b - 1] : 0, hi = start[b];
+                    int less = 0, eqb = 0;
+                    for (int q = lo; q < hi; ++q)
+                    {
+                        const int kk = bkey[q];
+                        less += kk < k;
+                        eqb += (kk == k) & (q < p);
+                    }
+                    const int j = lo + less + eqb;
+                    list[p] = (unsigned short)j;
+                    if (eqb == 0)
+                        atomicOr(&hb[j >> 5], 1u << (j & 31));
+                }
+                bar();
+                int hcarry = 0;
+                for (int w0 = 0; w0 < nW; w0 += nthr)
+                {
+                    const int w = w0 + tid;
+                    const int c = (w < nW) ? __popc(hb[w]) : 0;
+                    int tot, ex;
+                    if (nthr == 32)
+                    {
+                        int incl = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1)
+                        {
+                            const int t = __shfl_up_sync(kFull, incl, o);
+                            if (lane >= o)
+                                incl += t;
+                        }
+                        ex = incl - c;
+                        tot = __shfl_sync(kFull, incl, 31);
+                    }
+                    else
+                        ex = block_excl_scan(c, warp_tot, &tot);
+                    if (w < nW)
+                        hpre[w] = hcarry + ex;
+                    hcarry += tot;
+                }
+                bar();
+                // heads write their entry of C, then the repeats are added onto it
+                for (int pass = 0; pass < 2; ++pass)
+                {
+                    for (int p = tid; p < ne; p += nthr)
+                    {
+                        const int j = list[p];
+                        const unsigned word = hb[j >> 5];
+                        const bool head = (word >> (j & 31)) & 1u;
+                        if (head != (pass == 0))
+                            continue;
+                        const int dest = out + hpre[j >> 5] + __popc(word & ((2u << (j & 31)) - 1u)) - 1;
+                        const int sl = idx[p];
+                        if (head)
+                        {
+                            Cc[dest] = bkey[p];
+                            Cv[dest] = vals[sl];
+                        }
+                        else
+                            atomicAdd(&Cv[dest], vals[sl]);
+                        keys[sl] = -1; // leave the table clean for the next row
+                        if (!solo)
+                            vals[sl] = T(0);
+                    }
+                    bar();
+                }
+                for (int w = tid; w < 2 * nW; w += nthr) // the scratch lies in the table's value array: back to zero
+                    hb[w] = 0u;
+            }
+            else
             for (int p = tid; p < n; p += nthr)
             {
                 const int sl = idx[p];
