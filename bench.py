@@ -848,7 +848,9 @@ def main():
         ba = bytes_alg(A, B, nnzC_total)
         kern_ms = float(np.mean(num_ms))
         # per-rank share of the compulsory traffic for the kernel's roofline (rank 0's last slice)
-        ba_rank = bytes_alg(Ablk, B if mode in ("single", "broadcast") else B.rows(k0, k1), int(last[3].numel()))
+        # (a rank that cuts its block into slices: the A rows of the LAST slice, whose numeric time kern_ms is)
+        A_last = Ablk if len(slices) == 1 else Ablk.rows(last[0], last[1])
+        ba_rank = bytes_alg(A_last, B if mode in ("single", "broadcast") else B.rows(k0, k1), int(last[3].numel()))
         achieved = ba_rank / (kern_ms * 1e-3) / 1e9
         nb = {k: v for k, v in stats["num_bins"].items() if v and k != "EMPTY"}
         kernels = sorted({NUM_KERNEL.get(k, k) for k in nb})
