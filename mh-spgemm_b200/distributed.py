@@ -29,13 +29,14 @@ def row_work(A: CSR, B: CSR) -> np.ndarray:
 
 def row_cost(work: np.ndarray) -> np.ndarray:
     """Balancing weight per row of A: its intermediate products, inflated for long rows.
-    Measured on 8 B200 (profiles/r2_scaling.md, R-MAT scale 22 split by raw product count): a
-    rank whose rows average 2 000 products spent 88 ps per product, one with 300-product rows
-    44 ps -- long rows go through larger hash tables, more probe rounds and longer sorts, and
-    the rank that owns the hub rows set the step time.  cost = p * (1 + min(p, 6000) / 1500)
-    reproduces the measured per-rank times to within 5 %."""
+    Measured on 8 B200 (profiles/r2_scaling.md): long rows go through larger hash tables, more probe
+    rounds and longer sorts, and the rank that owns the hub rows set the step time.  R-MAT scale 24
+    split by the first model (p * (1 + min(p, 6000) / 1500), fitted at scale 22): the ranks spent
+    49 / 62 / 71 / 84 / 136 ps per product at 341 / 600 / 1 010 / 1 362 / 2 647 products per row on
+    average -- linear, 36 + 0.038 p -- and rank 0 (the hub rows) took 128 ms against 91 ms for the rest.
+    cost = p * (1 + min(p, 12000) / 950) is that line."""
     w = work.astype(np.float64)
-    return w * (1.0 + np.minimum(w, 6000.0) / 1500.0)
+    return w * (1.0 + np.minimum(w, 12000.0) / 950.0)
 
 
 def snap_to_pattern_change(A: CSR, bounds: np.ndarray) -> np.ndarray:
