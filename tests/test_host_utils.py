@@ -88,3 +88,17 @@ def test_perturbed_fem_breaks_the_twins():
     assert twins(A) == A.M // 3 * 2 and twins(P) < A.M // 50
     Q = G.fem3d_perturbed(4, 4, 12, 3, drop=0.10, seed=3)
     assert np.array_equal(P.col, Q.col) and np.array_equal(P.val, Q.val)  # seeded
+
+
+def test_rmat_device_generator_is_seeded_and_canonical():
+    """The torch-side R-MAT generator of the full-size configs[4] run (here on the CPU device): canonical
+    CSR, same matrix for the same seed (every rank of a job draws its own copy), R-MAT skew present."""
+    A = G.rmat_device(12, 1 << 12, 16 << 12, 0.45, 0.15, 0.15, seed=5, device="cpu")
+    B = G.rmat_device(12, 1 << 12, 16 << 12, 0.45, 0.15, 0.15, seed=5, device="cpu")
+    assert A.is_canonical() and (A.M, A.N) == (4096, 4096) and 0.8 * (16 << 12) < A.nnz <= (16 << 12)
+    assert np.array_equal(A.ptr, B.ptr) and np.array_equal(A.col, B.col) and np.array_equal(A.val, B.val)
+    assert A.val.min() >= 0.5 and A.val.max() < 1.5
+    deg = np.diff(A.ptr)
+    assert deg[:64].sum() > 8 * deg[-64:].sum()  # a = .45: the head rows are the heavy ones
+    C = G.rmat_device(12, 1 << 12, 16 << 12, 0.45, 0.15, 0.15, seed=6, device="cpu")
+    assert C.nnz != A.nnz or not np.array_equal(C.col, A.col)
