@@ -406,9 +406,24 @@ int build_mask_matrix(mhb_context *h, int K, int nnzB, const int *Bp, const int 
         if (nnz > 0)
         {
             LAUNCH(h, k_mask_rowstarts, cdiv(K, 256), 256, 0, K, Bp, oflags);
-            LAUNCH(h, k_mask_build, mask_chunks(nnz), kMaskThreads, 0, Bc, nnz, nW, oflags, wp, h->tilecol.as<int>(),
-                   h->tilemask.as<unsigned>(), reinterpret_cast<unsigned *>(base + kCtrlOffset),
-                   reinterpret_cast<unsigned long long *>(base + kStatusOffset), mask_chunks(nnz), ntiles_dev);
+            unsigned *ctrl = reinterpret_cast<unsigned *>(base + kCtrlOffset);
+            unsigned long long *status = reinterpret_cast<unsigned long long *>(base + kStatusOffset);
+            const int nch = mask_chunks(nnz);
+            if (h->mask_onepass == 2)
+            {
+                // two passes around a scan of the per-chunk tile counts (they live in the status words)
+                int *ct = reinterpret_cast<int *>(status), *cpfx = ct + nch + 1;
+                LAUNCH(h, k_mask_build<1>, nch, kMaskThreads, 0, Bc, nnz, nW, oflags, wp, h->tilecol.as<int>(),
+                       h->tilemask.as<unsigned>(), ctrl, status, nch, ntiles_dev, ct, (const int *)cpfx);
+                int rc = run_scan(h, LoadInt{ct}, nch, cpfx, 0, ntiles_dev);
+                if (rc)
+                    return rc;
+                LAUNCH(h, k_mask_build<2>, nch, kMaskThreads, 0, Bc, nnz, nW, oflags, wp, h->tilecol.as<int>(),
+                       h->tilemask.as<unsigned>(), ctrl, status, nch, ntiles_dev, ct, (const int *)cpfx);
+            }
+            else
+                LAUNCH(h, k_mask_build<0>, nch, kMaskThreads, 0, Bc, nnz, nW, oflags, wp, h->tilecol.as<int>(),
+                       h->tilemask.as<unsigned>(), ctrl, status, nch, ntiles_dev, (int *)nullptr, (const int *)nullptr);
         }
         LAUNCH(h, k_mask_rows, cdiv((long long)K + 1, 256), 256, 0, K, nnz, Bp, Bc, (const unsigned *)oflags,
                (const int *)wp, (const long long *)ntiles_dev, (const int *)h->tilecol.as<int>(),
@@ -901,6 +916,8 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
                 long long fused_capacity = -1)
 {
     h->fused_pending = false;
+    if (h->into.active && h->into.pending)
+        return fail(h, MHB_ERR_ARG, "a mhb_spgemm_into_begin_* is outstanding on this handle: call mhb_spgemm_into_end first");
     if (M < 0 || K < 0 || N < 0 || nnzA < 0 || nnzB < 0)
         return fail(h, MHB_ERR_ARG, "negative dimension");
     if (!Ap || !Bp || !Cp || (nnzA > 0 && !Ac) || (nnzB > 0 && !Bc))
@@ -1121,6 +1138,8 @@ int prepare_a_twins(mhb_context *h)
 template <typename T>
 int do_numeric(mhb_context *h, const T *Av, const T *Bv, int *Cc, T *Cv, bool sync)
 {
+    if (h->into.active && h->into.pending)
+        return fail(h, MHB_ERR_ARG, "a mhb_spgemm_into_begin_* is outstanding on this handle: call mhb_spgemm_into_end first");
     if (!h->have_pattern)
         return fail(h, MHB_ERR_ARG, "mhb_numeric called without a successful mhb_symbolic");
     if (h->nnzC > 0 && (!Av || !Bv || !Cc || !Cv))
@@ -1159,6 +1178,8 @@ int into_begin(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, con
                const int *Bp, const int *Bc, const T *Bv, int *Cp, int *Cc, T *Cv, long long capacity)
 {
     IntoCall &ic = h->into;
+    if (ic.active && ic.pending)
+        return fail(h, MHB_ERR_ARG, "a mhb_spgemm_into_begin_* is outstanding on this handle: call mhb_spgemm_into_end first");
     ic = IntoCall{};
     if (capacity < 0 || (capacity > 0 && (!Cc || !Cv)))
         return fail(h, MHB_ERR_ARG, "null output pointer / negative capacity");
@@ -1284,10 +1305,12 @@ int do_spgemm_into(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap,
     if (!nnzC)
         return fail(h, MHB_ERR_ARG, "null nnzC");
     *nnzC = 0;
+    const bool outstanding = h->into.active && h->into.pending;
     int rc = into_begin<T>(h, M, K, N, nnzA, Ap, Ac, Av, nnzB, Bp, Bc, Bv, Cp, Cc, Cv, capacity);
     if (rc)
     {
-        h->into.active = false;
+        if (!outstanding)
+            h->into.active = false;
         return rc;
     }
     return into_end<T>(h, nnzC);

@@ -238,21 +238,31 @@ __device__ __forceinline__ long long chained_scan_lookback(unsigned long long *s
 
 // ctrl[0] = chunk ticket counter (zeroed with the scalars); status[nchunks] zeroed likewise;
 // flags[] holds the row-start bits on entry and the complete tile-start flags on exit.
+// MODE 0: the one-pass builder (chunks by ticket, chained scan).  MODE 1 / MODE 2: the same work as two
+// passes around an ordinary scan of the per-chunk tile counts -- 1 forms the flags and counts the
+// tiles of chunk blockIdx.x (chunk_tiles), 2 takes the chunk's offset from chunk_prefix and does the
+// rest.  B.col is read twice (the second time from L2), but no block waits for another: the look-back
+// chain is what bounds MODE 0 (issue 30 %, two thirds of the stall samples at its barriers).
+#pragma nv_diag_suppress 128 // MODE 1 returns before the second half of the kernel
+template <int MODE>
 __global__ void __launch_bounds__(kMaskThreads, 4)
     k_mask_build(const int *__restrict__ Bc, long long nnz, long long nwords, unsigned *flags,
                  int *__restrict__ wordprefix, int *__restrict__ tilecol, unsigned *__restrict__ tilemask,
                  unsigned *__restrict__ ctrl, unsigned long long *__restrict__ status, int nchunks,
-                 long long *__restrict__ total64)
+                 long long *__restrict__ total64, int *__restrict__ chunk_tiles, const int *__restrict__ chunk_prefix)
 {
     pdl_prologue();
     constexpr int WPW = kMaskWordsPerWarp, NW = kMaskThreads / 32;
     __shared__ int sh_chunk;
     __shared__ int sh_warp[NW];
     __shared__ long long sh_look[NW + 2];
-    if (threadIdx.x == 0)
-        sh_chunk = (int)atomicAdd(ctrl, 1u);
-    __syncthreads();
-    const int chunk = sh_chunk;
+    if (MODE == 0)
+    {
+        if (threadIdx.x == 0)
+            sh_chunk = (int)atomicAdd(ctrl, 1u);
+        __syncthreads();
+    }
+    const int chunk = MODE == 0 ? sh_chunk : (int)blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     // positions are 32-bit: nnz(B) < 2^31 by the int32 CSR contract, and a chunk overruns it by < 2^12
     const unsigned w0 = (unsigned)chunk * kMaskChunkWords + (unsigned)warp * WPW; // first word of this warp
@@ -287,6 +297,25 @@ __global__ void __launch_bounds__(kMaskThreads, 4)
         f[i] = __ballot_sync(kFull, start) | rowbits[i];
         if (i < WPW)
             tiles += __popc(f[i]);
+    }
+    if (MODE == 1)
+    {
+#pragma unroll
+        for (int i = 0; i < WPW; ++i)
+            if (lane == 0 && w0 + i < (unsigned)nwords)
+                flags[w0 + i] = f[i];
+        if (lane == 0)
+            sh_warp[warp] = tiles;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int agg = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+                agg += sh_warp[w];
+            chunk_tiles[chunk] = agg;
+        }
+        return;
     }
     // The masks are formed BEFORE the look-back (they need no global position), so that the shuffle
     // work of this chunk overlaps the latency of its predecessors' status words; behind the
@@ -329,9 +358,15 @@ __global__ void __launch_bounds__(kMaskThreads, 4)
 #pragma unroll
     for (int w = 0; w < NW; ++w)
         agg += sh_warp[w];
-    const long long excl = chained_scan_lookback<NW>(status, chunk, agg, sh_look);
-    if (threadIdx.x == 0 && chunk == nchunks - 1)
-        *total64 = excl + agg;
+    long long excl;
+    if (MODE == 0)
+    {
+        excl = chained_scan_lookback<NW>(status, chunk, agg, sh_look);
+        if (threadIdx.x == 0 && chunk == nchunks - 1)
+            *total64 = excl + agg;
+    }
+    else
+        excl = chunk_prefix[chunk]; // (the scan has written the total)
     long long run = excl;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
@@ -358,6 +393,8 @@ __global__ void __launch_bounds__(kMaskThreads, 4)
         run += __popc(fi);
     }
 }
+
+#pragma nv_diag_default 128
 
 // Tile offsets, the per-row descriptor {nnz, tiles, first col, last col} and the twin flag
 // (same tile list as the previous row) of every row of B, one thread per row.

@@ -747,3 +747,45 @@ def test_host_path_row_chunks(orc, name, chunks):
     for _ in range(2):  # second call: speculative symbolic in front of the chunked numeric
         assert_matches(orc, t.spgemm_host(A, B), Cp, Cc, Cv)
     t.release()
+
+
+def test_one_outstanding_begin_per_handle(orc):
+    """A second call on a handle whose mhb_spgemm_into_begin has not been ended is refused instead of
+    trampling the workspace of the queued one; end still delivers the first result."""
+    A = G.fem3d(4, 4, 10, 3, seed=5)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    t = api.Tool(0)
+    dA = [api.DeviceArray(x) for x in (A.ptr, A.col, A.val)]
+    dC = (api.DeviceArray(count=A.M + 1, dtype=np.int32), api.DeviceArray(count=int(Cp[-1]), dtype=np.int32),
+          api.DeviceArray(count=int(Cp[-1]), dtype=np.float64))
+    args = (A.M, A.N, A.N, dA[0], dA[1], dA[2], dA[0], dA[1], dA[2], dC[0], dC[1], dC[2])
+    assert t.spgemm_into(*args) == Cp[-1]          # first call of the shape: ordinary path
+    t.spgemm_into_begin(*args)                      # steady state: queued, not waited for
+    with pytest.raises(api.MhbError):
+        t.spgemm_into_begin(*args)
+    with pytest.raises(api.MhbError):
+        t.symbolic(A.M, A.N, A.N, dA[0], dA[1], dA[0], dA[1])
+    assert t.spgemm_into_end() == Cp[-1]
+    assert_matches(orc, CSR(A.M, A.N, dC[0].numpy(), dC[1].numpy(), dC[2].numpy()), Cp, Cc, Cv)
+    t.release()
+
+
+@pytest.mark.parametrize("name", ["fem", "rmat14", "dense_rows", "poisson32", "road", "ragged", "empty", "one_row"])
+def test_mask_builder_modes_agree(orc, name):
+    """The three builders of B's mask matrix -- round 1's five-kernel chain (0), the one-pass chained scan
+    (1) and the two passes around an ordinary scan (2) -- give the same tileptr / tilecol / tilemask, and the
+    SpGEMM on top of each is the oracle's."""
+    A, B = INPUTS[name]()
+    B = A if B is None else B
+    Cp, Cc, Cv = orc.spgemm(A, B)
+    got = {}
+    for mode in (0, 1, 2):
+        t = api.Tool(0)
+        t.set_option("mask_onepass", mode)
+        dBp, dBc = api.DeviceArray(B.ptr), api.DeviceArray(B.col)
+        got[mode] = t.mask_matrix_B(B.M, B.N, dBp, dBc)
+        assert_matches(orc, t.spgemm_host(A, B), Cp, Cc, Cv)
+        t.release()
+    for mode in (0, 2):
+        for a, b in zip(got[1], got[mode]):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), f"mask builder mode {mode} differs from mode 1"
