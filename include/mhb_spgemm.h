@@ -84,7 +84,8 @@ int mhb_set_stream(mhb_handle_t h, void *cuda_stream);
  * "count_probes" (0): count failed hash probes into mhb_stats.hash_probes / sym_hash_probes;
  * "speculate" (1): a call with the shape of the previous one launches its symbolic kernels from
  * that call's bin sizes (one host read per SpGEMM instead of two; verified, re-run on a miss);
- * "mask_onepass" (1): one-pass mask builder (0: the round-1 five-kernel chain);
+ * "mask_onepass" (2): builder of B's mask matrix -- 2: two passes over B.col around a scan of the per-chunk tile
+ * counts, 1: one pass with a chained (look-back) scan, 0: the round-1 five-kernel chain;
  * "row_chunks" (2, at most 8) / "row_chunk_bytes" (32 MiB): mhb_spgemm_host_* runs the numeric phase in
  * that many row chunks (sizes 1 : 2 : 4 ... by nnz) when C.col + C.val are at least that large, and
  * downloads a finished chunk while the next one computes (1: off). */

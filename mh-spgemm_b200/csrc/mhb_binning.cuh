@@ -99,25 +99,29 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Load in, long long 
     pdl_prologue();
     __shared__ long long sh[32];
     __shared__ int warp_tot[32];
-    // offset of this block = sum of the preceding block sums
+    // offset of this block = sum of the preceding block sums (blocksums == nullptr: the scan is one
+    // block, launched alone -- no block-sum pass in front of it; the total falls out of the scan below)
     long long pre = 0, all = 0;
-    for (int b = threadIdx.x; b < nblocks; b += kScanThreads)
+    if (blocksums)
     {
-        long long v = blocksums[b];
-        all += v;
-        if (b < (int)blockIdx.x)
-            pre += v;
-    }
-    pre = block_reduce_sum(pre, sh);
-    if (blockIdx.x == gridDim.x - 1)
-    {
-        all = block_reduce_sum(all, sh);
-        if (threadIdx.x == 0)
+        for (int b = threadIdx.x; b < nblocks; b += kScanThreads)
         {
-            if (total64)
-                *total64 = all;
-            if (write_total)
-                out[n] = sat_i32(all);
+            long long v = blocksums[b];
+            all += v;
+            if (b < (int)blockIdx.x)
+                pre += v;
+        }
+        pre = block_reduce_sum(pre, sh);
+        if (blockIdx.x == gridDim.x - 1)
+        {
+            all = block_reduce_sum(all, sh);
+            if (threadIdx.x == 0)
+            {
+                if (total64)
+                    *total64 = all;
+                if (write_total)
+                    out[n] = sat_i32(all);
+            }
         }
     }
     // thread t owns kScanItems consecutive items
@@ -158,6 +162,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(Load in, long long 
     }
     __syncthreads();
     long long run = pre + warp_tot[threadIdx.x >> 5] + (incl - tsum);
+    if (!blocksums && threadIdx.x == kScanThreads - 1)
+    {
+        const long long total = run + tsum;
+        if (total64)
+            *total64 = total;
+        if (write_total)
+            out[n] = sat_i32(total);
+    }
 #pragma unroll
     for (int it = 0; it < kScanItems; ++it)
     {

@@ -155,7 +155,8 @@ struct mhb_context
     int fused_planned_tileflop = 0;
     int fused_calls = 0;
     IntoCall into;
-    int mask_onepass = 1;                // option "mask_onepass": one-pass mask builder (0: the round-1 five-kernel chain)
+    int mask_onepass = 2;                // option "mask_onepass": 2 = two passes around a scan of the chunk counts, 1 = one pass
+                                         // with a chained scan, 0 = the round-1 five-kernel chain
     int count_probes = 0;                // option "count_probes": hash kernels count failed probes (HASH_CONFLICT)
     bool asame_early = false;            // A's twin flags were computed beside the mask build (A is not B)
     int row_twins = 0;                   // option "row_twins": dense-window A-row twin fusion (slower: 8 warps/SM)
@@ -312,8 +313,13 @@ int run_scan(mhb_context *h, Load in, long long n, int *out, int write_total, lo
     }
     int nb = cdiv(n, kScanTile);
     long long *bs = h->scan_tmp.as<long long>();
+    if (nb == 1) // one tile: the scan kernel alone
+    {
+        LAUNCH(h, k_scan_apply<Load>, 1, kScanThreads, 0, in, n, (const long long *)nullptr, 1, out, write_total, total64_dev);
+        return MHB_OK;
+    }
     LAUNCH(h, k_scan_blocksums<Load>, nb, kScanThreads, 0, in, n, bs);
-    LAUNCH(h, k_scan_apply<Load>, nb, kScanThreads, 0, in, n, bs, nb, out, write_total, total64_dev);
+    LAUNCH(h, k_scan_apply<Load>, nb, kScanThreads, 0, in, n, (const long long *)bs, nb, out, write_total, total64_dev);
     return MHB_OK;
 }
 
