@@ -623,7 +623,7 @@ int launch_symbolic_bins(mhb_context *h, bool spec)
 template <typename T>
 size_t hash_list_smem(int S)
 {
-    return ((size_t)S * (sizeof(T) + 4) + (size_t)(S / 2 + 4) * 4 + (size_t)(S / 8) * 5 * (4 + 2 + 2) + 15) / 16 * 16;
+    return ((size_t)S * (sizeof(T) + 4) + (size_t)(S / 4 + 4) * 4 + (size_t)(S / 8) * 5 * (4 + 2 + 2) + 15) / 16 * 16;
 }
 
 template <typename T>

@@ -1243,7 +1243,7 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
     int np = 0;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ int warp_tot[32];
-    const int S = 1 << logS, NBmax = S >> 1, nmax = (S >> 3) * 5;
+    const int S = 1 << logS, NBmax = S >> 2, nmax = (S >> 3) * 5;
     T *vals = reinterpret_cast<T *>(sm_raw + (WROWS ? (size_t)(threadIdx.x >> 5) * table_bytes : 0));
     int *keys = reinterpret_cast<int *>(vals + S);
     int *start = keys + S;         // [NB + 1] bucket counts -> bucket begins -> bucket ends
@@ -1279,11 +1279,8 @@ __global__ void __launch_bounds__(WROWS ? 128 : 1024, WROWS ? 10 : 1) k_num_hash
         // is that of the bin's largest table; a smaller row uses a prefix of it, so its bucket
         // arrays, scans and probe cycles are sized by the row, not by the bin)
         const int lS = min(logS, max(5, ceil_log2_dev((n * 8 + 4) / 5)));
-        // S/2 buckets (~1.2 keys per bucket at fill 5/8): the rank loop below is quadratic in the bucket size, and
-        // with S/4 buckets it was a third of this kernel's instructions on power-law inputs, whose columns
-        // cluster (profiles/r2z_hash_kernels_R_after.md)
-        const int NB = 1 << (lS - 1);
-        const int sh = max(0, ceil_log2_dev(W) - (lS - 1));
+        const int NB = 1 << (lS - 2);
+        const int sh = max(0, ceil_log2_dev(W) - (lS - 2));
         for (int b = tid; b <= NB; b += nthr)
             start[b] = 0;
         if (tid == 0)
