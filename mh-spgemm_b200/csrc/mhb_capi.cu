@@ -976,8 +976,17 @@ int do_symbolic(mhb_context *h, int M, int K, int N, int nnzA, const int *Ap, co
     if (M > 0)
     {
         double avg = (double)nnzA / M;
-        // twin flags of A's rows, when they are known this early: B's flags (family 1) if A is B
-        const unsigned char *tw = (h->sym_twins && Ap == Bp && Ac == Bc) ? h->bsame.as<unsigned char>() : nullptr;
+        // twin flags of A's rows: B's flags (family 1) if A is B, else the comparison that ran on the
+        // helper stream beside the mask build (long finished: joined here instead of before the symbolic bins)
+        const unsigned char *tw = nullptr;
+        if (h->sym_twins && Ap == Bp && Ac == Bc)
+            tw = h->bsame.as<unsigned char>();
+        else if (h->sym_twins && h->asame_early)
+        {
+            if (!h->serial)
+                CU(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+            tw = h->asame_buf.as<unsigned char>();
+        }
         if (avg > 12.0)
             LAUNCH(h, k_arow_metrics<32>, std::min(cdiv((long long)M * 32, 256), h->num_sms * 16), 256, 0, M, Ap, Ac, h->binfo.as<int4>(),
                    h->arow.as<int4>(), h->binid.as<unsigned char>(), Cp, scal, h->force_sym, tw);
