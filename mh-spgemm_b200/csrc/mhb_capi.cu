@@ -5,8 +5,12 @@
 // Host-path design (vs the reference's 9 cudaMalloc, 12 stream creations, 7 blocking D2H
 // copies and 7 cudaDeviceSynchronize per call): one handle-owned, grow-only
 // workspace (no allocation in steady state), one stream, bin offsets computed on the
-// device, and exactly two small D2H reads per SpGEMM: the symbolic bin sizes, and
-// nnz(C) together with the numeric bin sizes (the hand-off the contract requires).
+// device.  Host reads per SpGEMM: two small ones in the symbolic phase on the first call of a
+// shape (symbolic bin sizes; nnz(C) + numeric bin sizes, the hand-off the contract requires);
+// ONE when the call has the shape of the previous one (the symbolic kernels are launched
+// speculatively from that call's bin sizes, RowList); and for mhb_spgemm_into_* (caller-owned
+// C arrays) a single synchronisation at the very end -- both phases launched speculatively,
+// verified by k_fused_gate on the device, redone the ordinary way on a miss.
 #include <cuda_runtime.h>
 
 #include <algorithm>
