@@ -789,3 +789,31 @@ def test_mask_builder_modes_agree(orc, name):
     for mode in (0, 2):
         for a, b in zip(got[1], got[mode]):
             assert np.array_equal(np.asarray(a), np.asarray(b)), f"mask builder mode {mode} differs from mode 1"
+
+
+def test_sharded_spgemm_binds_the_callers_stream(orc):
+    """ShardedSpGEMM (the torch.distributed layer) on torch's DEFAULT stream without any pre-binding by the
+    caller: B's image is produced by torch ops on that stream right before the step, the C arrays come
+    from torch's allocator, and the handle must run on the same stream (legacy default stream = handle 0,
+    which Tool.set_stream maps to cudaStreamLegacy).  ADVICE r1: the class used to leave the handle on
+    its own stream, unordered against the exchange."""
+    import torch
+    from mh_spgemm_b200.distributed import ShardedSpGEMM, b_views, pack_b
+    A = G.fem3d(4, 4, 16, 3, seed=61)
+    Cp, Cc, Cv = orc.spgemm(A, A)
+    dev = torch.device("cuda", 0)
+    t = api.Tool(0)
+    sh = ShardedSpGEMM(t, 0, 1, dev)
+    packed, _ = pack_b(A)
+    ap, ac, av = (torch.from_numpy(x).to(dev) for x in (A.ptr, A.col, A.val))
+    for step in range(3):
+        # the "exchange": B's image is rewritten on the default stream just before the multiply (scaled values)
+        Bbuf = torch.zeros_like(packed, device=dev)
+        Bbuf.copy_(packed.to(dev))
+        bp, bc, bv = b_views(Bbuf, A.M, A.nnz, torch.float64)
+        bv.mul_(float(step + 1))
+        cp, cc, cv, off, tot = sh.step((A.M, ap, ac, av), Bbuf, A.M, A.N, A.nnz, torch.float64)
+        assert off == 0 and tot == Cp[-1]
+        got = CSR(A.M, A.N, cp.cpu().numpy(), cc.cpu().numpy(), cv.cpu().numpy())
+        assert_matches(orc, got, Cp, Cc, Cv * float(step + 1))
+    t.release()
