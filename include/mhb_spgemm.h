@@ -109,7 +109,7 @@ int mhb_numeric_f64(mhb_handle_t h, const double *dA_val, const double *dB_val,
 int mhb_numeric_f32(mhb_handle_t h, const float *dA_val, const float *dB_val,
                     int *dC_col, float *dC_val);
 
-/* One-shot MH_spgemm: symbolic, cudaMalloc of C, numeric.  *dC_ptr/*dC_col/*dC_val are
+/* One-shot MH_spgemm: symbolic, cudaMalloc of C, numeric.  The arrays behind dC_ptr, dC_col and dC_val are
  * caller-owned afterwards (cudaFree / mhb_device_free), as CSR::d_release_csr expects
  * (src/CSR.cu:14-22). */
 int mhb_spgemm_f64(mhb_handle_t h, int M, int K, int N,

@@ -82,3 +82,15 @@ def test_product_never_imports_the_oracle():
                 if needle in text:
                     bad.append((f, needle))
     assert not bad, bad
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mhb_spgemm.h is the FFI surface: it must compile as C99 with no C++ and no CUDA headers."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mhb_spgemm.h"\n'
+                   "int main(void) { mhb_handle_t h = 0; mhb_shard_t s = 0; mhb_timing t; mhb_stats st; (void)h; (void)s;\n"
+                   "  (void)t; (void)st; return (MHB_OK == 0 && MHB_ERR_CAPACITY == 5 && MHB_SHARD_BLOB_BYTES == 128) ? 0 : 1; }\n")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                          "-o", str(tmp_path / "hdr"), str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert subprocess.run([str(tmp_path / "hdr")]).returncode == 0
