@@ -53,5 +53,17 @@ def build_compat_driver() -> str:
     return out
 
 
+def build_shard_driver() -> str:
+    """tests/cpp/shard_driver.cpp: a plain C++ (g++, no CUDA headers) two-process caller of mhb_shard_*."""
+    root = os.path.join(HERE, "..")
+    src = os.path.join(root, "tests", "cpp", "shard_driver.cpp")
+    out = os.path.join(root, "tests", "cpp", "shard_driver")
+    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), "-o", out, src,
+                           "-L", HERE, "-lmhb_spgemm", "-Wl,-rpath,$ORIGIN/../../mh-spgemm_b200"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

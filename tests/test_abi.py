@@ -94,3 +94,11 @@ def test_header_is_plain_c(tmp_path):
                           "-o", str(tmp_path / "hdr"), str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert subprocess.run([str(tmp_path / "hdr")]).returncode == 0
+
+
+def test_cpp_shard_driver_links():
+    """The plain C++ caller of the row-sharded API (tests/cpp/shard_driver.cpp: g++ only, no CUDA headers)
+    compiles against include/mhb_spgemm.h and links with the library; the -m gpu suite runs it."""
+    from importlib import import_module
+    exe = import_module("mh_spgemm_b200.build").build_shard_driver()
+    assert os.path.exists(exe)

@@ -817,3 +817,12 @@ def test_sharded_spgemm_binds_the_callers_stream(orc):
         got = CSR(A.M, A.N, cp.cpu().numpy(), cc.cpu().numpy(), cv.cpu().numpy())
         assert_matches(orc, got, Cp, Cc, Cv * float(step + 1))
     t.release()
+
+
+def test_cpp_shard_driver_two_ranks():
+    """Two forked C++ processes drive mhb_shard_* through the C ABI alone (peer windows, fused call in two
+    halves, device-side size post) and check their slices against a host Gustavson inside the driver."""
+    from importlib import import_module
+    exe = import_module("mh_spgemm_b200.build").build_shard_driver()
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.count("SHARD-CPP-OK") == 2, p.stdout[-2000:] + p.stderr[-2000:]
