@@ -154,3 +154,20 @@ def test_cost_weighted_partition_and_twin_snap():
     # snapping never moves a boundary of an input without twin rows
     assert np.array_equal(D.snap_to_pattern_change(R, b_cost), b_cost) or np.all(
         np.abs(D.snap_to_pattern_change(R, b_cost) - b_cost) <= 4)
+
+
+def test_row_cost_weights_long_rows_up():
+    """The balancing weight grows faster than the product count (long rows go through larger tables and
+    longer sorts) and saturates: a partition by cost gives the block that owns the hub rows fewer products
+    than a partition by raw products would."""
+    w = np.array([1, 10, 100, 1000, 12000, 100000], np.int64)
+    c = D.row_cost(w)
+    per_product = c / w
+    assert np.all(np.diff(per_product[:5]) > 0) and np.isclose(per_product[4], per_product[5])
+    A = G.rmat(14, 16000, 120000, a=0.55, b=0.15, c=0.15, seed=9)
+    work = D.row_work(A, A)
+    by_cost = D.partition_rows(D.row_cost(work), 4)
+    by_work = D.partition_rows(work, 4)
+    head = lambda b: int(work[b[0]:b[1]].sum())  # noqa: E731
+    assert head(by_cost) <= head(by_work)
+    assert by_cost[0] == 0 and by_cost[-1] == A.M and np.all(np.diff(by_cost) >= 0)
